@@ -1,0 +1,125 @@
+/*
+ * lz4b200.h -- C ABI of the B200-native LZ4 block codec for lzbench's chunked mode (-b#).
+ *
+ * Plain C, plain pointers and sizes: this is exactly what a reference-side binding links
+ * against (see INTEGRATION.md for the rows/wrappers a maintainer adds to
+ * _lzbench/compressors.cpp, compressors.h and lzbench.h).  Every entry point cites the
+ * reference interface it replaces.  There is no CPU fallback anywhere behind this header:
+ * every call either runs the sm_100a kernels or fails (negative return, message available
+ * from lz4b200_last_error()).
+ *
+ * Data layout (identical to the reference's chunk loops):
+ *   uncompressed image : chunk i at  sum(chunk_sizes[0..i))          (contiguous)
+ *   compressed image   : chunk i at  sum(compr_sizes[0..i))          (contiguous, no header)
+ *   each compressed chunk is one standard LZ4 block, or the raw bytes when
+ *   compr_sizes[i] == chunk_sizes[i]  (_lzbench/lzbench.cpp:284-289, :311-315).
+ */
+#ifndef LZ4B200_H
+#define LZ4B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LZ4B200_VERSION_STRING "0.1"
+
+typedef struct lz4b200_ctx lz4b200_ctx;
+
+/* ---- library ------------------------------------------------------------------------- */
+
+/* Library version string ("0.1"); the `version` column of the comp_desc[] row
+ * (_lzbench/lzbench.h:142-219). */
+const char* lz4b200_version(void);
+
+/* Thread-local message for the last failing call in this thread ("" if none). */
+const char* lz4b200_last_error(void);
+
+/* Worst-case size of one compressed chunk: n + n/255 + 16 (lz4/lz4.h:171 LZ4_COMPRESSBOUND;
+ * lz4/lz4.c LZ4_compressBound).  0 if n exceeds LZ4_MAX_INPUT_SIZE (lz4/lz4.h:170). */
+size_t lz4b200_compress_bound(size_t n);
+
+/* Number of CUDA devices visible, or a negative value if the runtime cannot be initialised. */
+int lz4b200_device_count(void);
+
+/* ---- context (replaces init_func / deinit_func, _lzbench/lzbench.h:114-115; precedent
+ *      lzbench_nvcomp_init/_deinit, _lzbench/compressors.cpp:1856-1914) ------------------- */
+
+/* Create a codec context bound to CUDA device `device`.  `max_total_bytes` and
+ * `max_chunk_bytes` are sizing hints (0 allowed): buffers grow on demand.  One context
+ * serves both directions; calls on one context must be serial (lzbench is single-threaded,
+ * _lzbench/lzbench.cpp:479-534).  Returns 0 or a negative error. */
+int lz4b200_create(int device, size_t max_total_bytes, size_t max_chunk_bytes, lz4b200_ctx** ctx);
+void lz4b200_destroy(lz4b200_ctx* ctx);
+
+/* ---- batched host-buffer entry points: the hot path ------------------------------------ */
+
+/* Replaces the whole of lzbench_compress (_lzbench/lzbench.cpp:266-298) for one codec:
+ * compresses n_chunks independent chunks of `in` (sizes chunk_sizes[]) into the contiguous
+ * concatenation `out`, fills compr_sizes[], stores a chunk raw iff its LZ4 block would be
+ * exactly chunk_sizes[i] bytes (:284-289).  Returns the total compressed size, 0 if it
+ * does not fit in out_capacity (:286), negative on CUDA failure.  Host pointers; copies
+ * to/from the device are inside the call. */
+int64_t lz4b200_compress_batch(lz4b200_ctx* ctx, const char* in, const size_t* chunk_sizes,
+                               size_t n_chunks, char* out, size_t out_capacity, size_t* compr_sizes);
+
+/* Replaces the whole of lzbench_decompress (_lzbench/lzbench.cpp:301-329): chunk i is
+ * copied raw iff compr_sizes[i] == chunk_sizes[i] (:311-315), otherwise decoded as one LZ4
+ * block of exactly chunk_sizes[i] bytes.  Returns the total decompressed size, or a value
+ * <= 0 if any chunk is malformed (:321; the bounds-checked decoder follows
+ * LZ4_decompress_safe's rules, lz4/lz4.c:2171, not LZ4_decompress_fast's trust). */
+int64_t lz4b200_decompress_batch(lz4b200_ctx* ctx, const char* in, const size_t* compr_sizes,
+                                 const size_t* chunk_sizes, size_t n_chunks, char* out);
+
+/* ---- device-resident entry points (inputs and outputs stay in HBM; used for the roofline
+ *      measurement and by callers that already hold data on the GPU) ----------------------- */
+
+/* All pointers are device pointers on the context's device; `stream` is a cudaStream_t
+ * (0 = default stream).  Size arrays are uint64_t.  Calls are asynchronous on `stream`.
+ * d_total_out receives the total compressed size.  Returns 0 on successful launch. */
+int lz4b200_compress_device(lz4b200_ctx* ctx, const void* d_in, const uint64_t* d_chunk_sizes,
+                            size_t n_chunks, size_t max_chunk_bytes, void* d_out,
+                            uint64_t* d_compr_sizes, uint64_t* d_total_out, void* stream);
+
+/* d_bad_chunks (may be NULL) receives the number of malformed chunks (0 = success). */
+int lz4b200_decompress_device(lz4b200_ctx* ctx, const void* d_in, const uint64_t* d_compr_sizes,
+                              const uint64_t* d_chunk_sizes, size_t n_chunks, size_t max_chunk_bytes,
+                              void* d_out, uint32_t* d_bad_chunks, void* stream);
+
+/* Number of kernels this library launched through `ctx` since creation (for bench.py's
+ * gpu_launches claim). */
+uint64_t lz4b200_launch_count(const lz4b200_ctx* ctx);
+
+/* Tunable: which kernel generation to run ("v0" warp-per-chunk baseline, "v1" tiled CTA
+ * kernels).  Returns 0, or -1 for an unknown name.  Default is the fastest verified one. */
+int lz4b200_set_option(lz4b200_ctx* ctx, const char* key, const char* value);
+
+/* ---- lzbench plugin-signature wrappers (drop-in comp_desc[] row "lz4_b200") -------------- */
+
+/* Exactly the typedefs at _lzbench/lzbench.h:113-115.  Called per chunk they run a
+ * one-chunk batch, so `lzbench -elz4_b200 -b64` works on an unpatched harness next to
+ * `-elz4` (_lzbench/compressors.cpp:343-362); INTEGRATION.md shows the <=30-line harness
+ * patch that hands the whole chunk list to the batched entry points instead. */
+char*   lzbench_lz4_b200_init(size_t insize, size_t level, size_t param2);
+void    lzbench_lz4_b200_deinit(char* workmem);
+int64_t lzbench_lz4_b200_compress(char* in, size_t insize, char* out, size_t outsize,
+                                  size_t level, size_t param2, char* workmem);
+int64_t lzbench_lz4_b200_decompress(char* in, size_t insize, char* out, size_t outsize,
+                                    size_t level, size_t param2, char* workmem);
+
+/* Batched forms behind the same workmem, for the patched harness: same arguments as
+ * lzbench_compress / lzbench_decompress minus the function pointer. */
+int64_t lzbench_lz4_b200_compress_batch(const size_t* chunk_sizes, size_t n_chunks, size_t* compr_sizes,
+                                        char* in, char* out, size_t outsize, char* workmem);
+int64_t lzbench_lz4_b200_decompress_batch(const size_t* chunk_sizes, const size_t* compr_sizes, size_t n_chunks,
+                                          char* in, char* out, char* workmem);
+
+/* ---- synthetic corpora; host-side, deterministic ----------------------- */
+int lz4b200_corpus_fill(int kind, uint64_t seed, uint64_t offset, uint64_t len, uint8_t* out, int n_threads);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

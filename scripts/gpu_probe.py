@@ -1,0 +1,47 @@
+"""Quick device-resident timing probe (not the bench): GB/s of uncompressed bytes per kernel generation."""
+import sys
+import time
+
+import numpy as np
+import torch
+
+import lzbench_b200 as L
+
+n = int(sys.argv[1]) << 20 if len(sys.argv) > 1 else 1024 << 20
+chunk = int(sys.argv[2]) if len(sys.argv) > 2 else 65536
+kinds = sys.argv[3].split(",") if len(sys.argv) > 3 else ["mixed"]
+gens = sys.argv[4].split(",") if len(sys.argv) > 4 else ["v0", "v1"]
+
+ctx = L.Lz4B200(0)
+for kind in kinds:
+    host = torch.empty(n, dtype=torch.uint8).pin_memory()
+    t0 = time.time(); L.corpus(kind, n, seed=2, out=host.numpy()); tg = time.time() - t0
+    d_in = host.cuda()
+    n_chunks = (n + chunk - 1) // chunk
+    cs = L.chunk_list(n, chunk).astype(np.int64)
+    d_cs = torch.from_numpy(cs).cuda()
+    d_out = torch.empty(L.get_compress_bound(n), dtype=torch.uint8, device="cuda")
+    d_compr = torch.empty(n_chunks, dtype=torch.int64, device="cuda")
+    d_total = torch.zeros(1, dtype=torch.int64, device="cuda")
+    d_back = torch.zeros(n, dtype=torch.uint8, device="cuda")
+    d_bad = torch.zeros(1, dtype=torch.int32, device="cuda")
+    s = torch.cuda.current_stream().cuda_stream
+    for gen in gens:
+        ctx.set_option("kernels", gen)
+        def comp(): ctx.compress_device(d_in, d_cs, n_chunks, chunk, d_out, d_compr, d_total, s)
+        def deco(): ctx.decompress_device(d_out, d_compr, d_cs, n_chunks, chunk, d_back, d_bad, s)
+        res = {}
+        for name, fn in (("compress", comp), ("decompress", deco)):
+            fn(); torch.cuda.synchronize()
+            ts = []
+            for _ in range(5):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+                ts.append(e0.elapsed_time(e1))
+            res[name] = min(ts)
+        total = int(d_total.item())
+        ok = bool(torch.equal(d_back, d_in)) and int(d_bad.item()) == 0
+        print(f"{kind} {n>>20}MiB chunk={chunk} {gen}: ratio={100*total/n:.2f}% "
+              f"compress {n/res['compress']/1e6:.1f} GB/s ({res['compress']:.2f} ms) "
+              f"decompress {n/res['decompress']/1e6:.1f} GB/s ({res['decompress']:.2f} ms) "
+              f"roundtrip_ok={ok} (corpus gen {tg:.1f}s)", flush=True)

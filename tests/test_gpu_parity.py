@@ -1,0 +1,220 @@
+"""GPU parity tests (run on the B200 box): every call goes through the C ABI of
+lzbench_b200/_lib/liblz4b200.so; the oracle (and oracle/_ref when it travelled) is the checker.
+
+Bars: decompression bit-exact; every GPU-compressed chunk decodes bit-exactly through the oracle
+decoder AND the reference's LZ4_decompress_safe / LZ4_decompress_fast; every oracle/reference
+compressed chunk decodes bit-exactly on the GPU; compressed size <= 1.03 x reference on the same
+chunking (BASELINE.json north_star)."""
+import ctypes as C
+import zlib
+
+import numpy as np
+import pytest
+
+import lzbench_b200 as L
+from tests import oracle_lib as O
+
+pytestmark = pytest.mark.gpu
+
+RATIO_TOLERANCE = 1.03
+
+CORPORA = [("mixed", 1), ("random", 4), ("repeat", 5), ("zero", 5)]
+
+
+def check_gpu_blocks_with_reference(data, packed, compr, cs):
+    off_p = off_u = 0
+    for z, n in zip(compr.tolist(), cs.tolist()):
+        z, n = int(z), int(n)
+        blk, plain = packed[off_p:off_p + z], data[off_u:off_u + n]
+        if z == n:                      # raw-stored chunk
+            assert np.array_equal(blk, plain)
+        else:
+            assert O.oracle_validate(blk, n) == 0, (off_u, z, n)
+            r, out = O.oracle_decompress(blk, n)
+            assert r == n and np.array_equal(out, plain), ("oracle decode", off_u)
+            if O.ref is not None:
+                r, out = O.ref_decompress_safe(blk, n)
+                assert r == n and np.array_equal(out, plain), ("LZ4_decompress_safe", off_u)
+                out = np.zeros(n + 64, dtype=np.uint8)
+                r = O.ref.LZ4_decompress_fast(blk.ctypes.data, out.ctypes.data, n)
+                assert r == z and np.array_equal(out[:n], plain), ("LZ4_decompress_fast", off_u)
+        off_p += z
+        off_u += n
+
+
+@pytest.mark.parametrize("kernels", ["v0", "v1"])
+@pytest.mark.parametrize("chunk", [4096, 65536, 100000, 1 << 20])
+@pytest.mark.parametrize("kind,seed", CORPORA)
+def test_compress_cross_decodes_and_ratio(gpu_ctx, kernels, chunk, kind, seed):
+    gpu_ctx.set_option("kernels", kernels)
+    n = 2 * (1 << 20) + 777                      # ragged last chunk
+    data = L.corpus(kind, n, seed=seed)
+    cs = L.chunk_list(n, chunk)
+    packed, compr, total = gpu_ctx.compress_batch(data, cs)
+    assert total > 0 and int(compr.sum()) == total
+    check_gpu_blocks_with_reference(data, packed[:total], compr, cs)
+    _, ref_compr = O.oracle_chunked_compress(data, cs)
+    assert total <= RATIO_TOLERANCE * int(ref_compr.sum()) + 64, (total, int(ref_compr.sum()))
+
+
+@pytest.mark.parametrize("kernels", ["v0", "v1"])
+@pytest.mark.parametrize("chunk", [4096, 65536, 100000, 1 << 20])
+@pytest.mark.parametrize("kind,seed", CORPORA)
+def test_decompress_reference_blocks_bit_exact(gpu_ctx, kernels, chunk, kind, seed):
+    gpu_ctx.set_option("kernels", kernels)
+    n = 2 * (1 << 20) + 777
+    data = L.corpus(kind, n, seed=seed)
+    cs = L.chunk_list(n, chunk)
+    packed, compr = O.oracle_chunked_compress(data, cs)
+    out, r = gpu_ctx.decompress_batch(packed, compr, cs)
+    assert r == n
+    assert np.array_equal(out, data)
+
+
+@pytest.mark.parametrize("kernels", ["v0", "v1"])
+def test_small_and_ragged_chunks(gpu_ctx, kernels):
+    gpu_ctx.set_option("kernels", kernels)
+    rng = np.random.default_rng(5)
+    sizes = [1, 2, 5, 11, 12, 13, 14, 15, 16, 17, 31, 32, 33, 63, 64, 65, 100, 255, 256, 270, 271, 1000,
+             4095, 4097, 65535, 65536, 65537, 65546, 65547, 70000]
+    sizes += [int(x) for x in rng.integers(1, 3000, 200)]
+    cs = np.asarray(sizes, dtype=np.uint64)
+    n = int(cs.sum())
+    for kind, seed in CORPORA:
+        data = L.corpus(kind, n, seed=seed)
+        packed, compr, total = gpu_ctx.compress_batch(data, cs)
+        check_gpu_blocks_with_reference(data, packed[:total], compr, cs)
+        out, r = gpu_ctx.decompress_batch(packed[:total], compr, cs)
+        assert r == n and np.array_equal(out, data)
+        p2, c2 = O.oracle_chunked_compress(data, cs)
+        out, r = gpu_ctx.decompress_batch(p2, c2, cs)
+        assert r == n and np.array_equal(out, data)
+
+
+@pytest.mark.parametrize("kernels", ["v0", "v1"])
+def test_raw_stored_chunks(gpu_ctx, kernels):
+    """compr_sizes[i] == chunk_sizes[i] means raw bytes (_lzbench/lzbench.cpp:311-315)."""
+    gpu_ctx.set_option("kernels", kernels)
+    data = L.corpus("mixed", 3 * 65536 + 100, seed=8)
+    cs = L.chunk_list(len(data), 65536)
+    packed, compr = O.oracle_chunked_compress(data, cs)
+    # replace chunk 1 by its raw bytes
+    parts = list(O.split_chunks(packed, compr))
+    parts[1] = data[65536:131072]
+    compr = compr.copy(); compr[1] = 65536
+    packed = np.concatenate(parts)
+    out, r = gpu_ctx.decompress_batch(packed, compr, cs)
+    assert r == len(data) and np.array_equal(out, data)
+
+
+@pytest.mark.parametrize("kernels", ["v0", "v1"])
+def test_kat_table_on_gpu(gpu_ctx, kernels):
+    gpu_ctx.set_option("kernels", kernels)
+    for name, blk, n, expect in O.KATS:
+        if n == 0:
+            continue                      # lzbench never forms empty chunks; covered by the oracle test
+        out, r = gpu_ctx.decompress_batch(blk, [len(blk)], [n])
+        if expect is None:
+            assert r <= 0, name
+        else:
+            assert r == n, name
+            assert out.tobytes() == expect, name
+
+
+@pytest.mark.parametrize("kernels", ["v0", "v1"])
+def test_corrupted_blocks_never_crash_and_match_oracle(gpu_ctx, kernels):
+    gpu_ctx.set_option("kernels", kernels)
+    rng = np.random.default_rng(13)
+    data = L.corpus("mixed", 8192, seed=3)
+    good = O.oracle_compress(data)
+    blocks, expect = [], []
+    for _ in range(512):
+        bad = good.copy()
+        for _ in range(int(rng.integers(1, 4))):
+            bad[int(rng.integers(0, len(bad)))] = int(rng.integers(0, 256))
+        blocks.append(bad)
+        r, out = O.oracle_decompress(bad, len(data))
+        expect.append((r == len(data), out))
+    # one batch with all of them: count of failures must match; then each alone for exactness
+    packed = np.concatenate(blocks)
+    compr = np.full(len(blocks), len(good), dtype=np.uint64)
+    cs = np.full(len(blocks), len(data), dtype=np.uint64)
+    out, r = gpu_ctx.decompress_batch(packed, compr, cs)
+    n_bad = sum(1 for ok, _ in expect if not ok)
+    assert (r == -n_bad) if n_bad else (r == len(data) * len(blocks))
+    out = out.reshape(len(blocks), len(data))
+    for i, (ok, ref_out) in enumerate(expect):
+        if ok:
+            assert np.array_equal(out[i], ref_out), i
+
+
+@pytest.mark.parametrize("kernels", ["v0", "v1"])
+def test_plugin_signature_wrappers(gpu_ctx, kernels):
+    """lzbench_lz4_b200_{init,compress,decompress,deinit}: the unpatched-harness path, one chunk per call."""
+    wm = L.lib.lzbench_lz4_b200_init(65536, 0, 0)
+    assert wm
+    try:
+        data = L.corpus("mixed", 200000, seed=4)
+        cs = L.chunk_list(len(data), 65536)
+        cap = L.get_compress_bound(65536)
+        out = np.zeros(cap, dtype=np.uint8)
+        back = np.zeros(65536, dtype=np.uint8)
+        off = 0
+        for n in cs.tolist():
+            n = int(n)
+            part = np.ascontiguousarray(data[off:off + n])
+            clen = L.lib.lzbench_lz4_b200_compress(part.ctypes.data, n, out.ctypes.data, cap, 0, 0, wm)
+            assert 0 < clen <= L.compress_bound(n)
+            assert O.oracle_validate(out[:clen], n) == 0
+            dlen = L.lib.lzbench_lz4_b200_decompress(out.ctypes.data, clen, back.ctypes.data, n, 0, 0, wm)
+            assert dlen == n and np.array_equal(back[:n], part)
+            off += n
+    finally:
+        L.lib.lzbench_lz4_b200_deinit(wm)
+
+
+def test_output_capacity_rule(gpu_ctx):
+    """lzbench_compress returns 0 when the image does not fit (_lzbench/lzbench.cpp:286)."""
+    data = L.corpus("random", 1 << 20, seed=4)
+    cs = L.chunk_list(len(data), 65536)
+    small = np.zeros(len(data), dtype=np.uint8)        # random data expands
+    _, _, total = gpu_ctx.compress_batch(data, cs, small)
+    assert total == 0
+
+
+@pytest.mark.parametrize("kernels", ["v0", "v1"])
+def test_device_resident_roundtrip_256m(gpu_ctx, kernels):
+    """Full-size property test: encode -> decode on the device, compare CRC of the whole image."""
+    import torch
+    gpu_ctx.set_option("kernels", kernels)
+    n = 256 << 20
+    chunk = 65536
+    host = torch.empty(n, dtype=torch.uint8).pin_memory()
+    L.corpus("mixed", n, seed=2, out=host.numpy())
+    d_in = host.cuda()
+    n_chunks = n // chunk
+    d_cs = torch.full((n_chunks,), chunk, dtype=torch.int64, device="cuda")
+    d_out = torch.empty(L.get_compress_bound(n), dtype=torch.uint8, device="cuda")
+    d_compr = torch.empty(n_chunks, dtype=torch.int64, device="cuda")
+    d_total = torch.zeros(1, dtype=torch.int64, device="cuda")
+    s = torch.cuda.current_stream().cuda_stream
+    gpu_ctx.compress_device(d_in, d_cs, n_chunks, chunk, d_out, d_compr, d_total, s)
+    torch.cuda.synchronize()
+    total = int(d_total.item())
+    assert int(d_compr.sum().item()) == total
+    assert 0.4 * n < total < 0.75 * n
+    d_back = torch.zeros(n, dtype=torch.uint8, device="cuda")
+    d_bad = torch.zeros(1, dtype=torch.int32, device="cuda")
+    gpu_ctx.decompress_device(d_out, d_compr, d_cs, n_chunks, chunk, d_back, d_bad, s)
+    torch.cuda.synchronize()
+    assert int(d_bad.item()) == 0
+    assert torch.equal(d_back, d_in)
+    # spot-check 64 chunks of the GPU image through the reference decoder
+    compr = d_compr.cpu().numpy().astype(np.uint64)
+    offs = np.concatenate([[0], np.cumsum(compr)[:-1]]).astype(np.int64)
+    packed = d_out[:total].cpu().numpy()
+    plain = host.numpy()
+    for i in np.linspace(0, n_chunks - 1, 64).astype(int):
+        blk = packed[offs[i]:offs[i] + int(compr[i])]
+        r, out = O.oracle_decompress(blk, chunk)
+        assert r == chunk and zlib.crc32(out.tobytes()) == zlib.crc32(plain[i * chunk:(i + 1) * chunk].tobytes())
