@@ -92,8 +92,16 @@ int lz4b200_decompress_device(lz4b200_ctx* ctx, const void* d_in, const uint64_t
  * gpu_launches claim). */
 uint64_t lz4b200_launch_count(const lz4b200_ctx* ctx);
 
+/* Per-launch device time of the codec kernel (the dominant kernel of each direction), measured
+ * with CUDA events on the launching stream.  Enable with lz4b200_set_option(ctx,"timing","1");
+ * every compress/decompress call then records one event pair (up to 256 between reads).  This
+ * call waits for the recorded launches, writes up to max_n durations in milliseconds in launch
+ * order, clears the list and returns how many were written (negative on error). */
+int lz4b200_kernel_times_ms(lz4b200_ctx* ctx, float* out_ms, int max_n);
+
 /* Tunable: which kernel generation to run ("v0" warp-per-chunk baseline, "v1" tiled CTA
- * kernels).  Returns 0, or -1 for an unknown name.  Default is the fastest verified one. */
+ * kernels).  Also "timing" = "0"/"1" (see above).  Returns 0, or -1 for an unknown key or value.
+ * Default kernels: the fastest verified generation. */
 int lz4b200_set_option(lz4b200_ctx* ctx, const char* key, const char* value);
 
 /* ---- lzbench plugin-signature wrappers (drop-in comp_desc[] row "lz4_b200") -------------- */

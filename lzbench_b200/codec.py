@@ -49,6 +49,8 @@ def _load() -> C.CDLL:
     L.lz4b200_decompress_device.argtypes = [vp, vp, vp, vp, sz, sz, vp, vp, vp]
     L.lz4b200_launch_count.restype = u64
     L.lz4b200_launch_count.argtypes = [vp]
+    L.lz4b200_kernel_times_ms.restype = C.c_int
+    L.lz4b200_kernel_times_ms.argtypes = [vp, vp, C.c_int]
     L.lz4b200_set_option.restype = C.c_int
     L.lz4b200_set_option.argtypes = [vp, C.c_char_p, C.c_char_p]
     L.lzbench_lz4_b200_init.restype = vp
@@ -158,6 +160,13 @@ class Lz4B200:
     def set_option(self, key: str, value: str):
         if lib.lz4b200_set_option(self._h, key.encode(), value.encode()) != 0:
             raise ValueError(last_error())
+
+    def kernel_times_ms(self):
+        buf = (C.c_float * 256)()
+        n = lib.lz4b200_kernel_times_ms(self._h, buf, 256)
+        if n < 0:
+            raise RuntimeError(last_error())
+        return [float(buf[i]) for i in range(n)]
 
     # -- host-buffer batched calls (the reference-facing hot path) -----------------------
     def compress_batch(self, inbuf, chunk_sizes, outbuf=None) -> Tuple[np.ndarray, np.ndarray, int]:

@@ -79,12 +79,15 @@ compress_v0_kernel(const u8* __restrict__ in, const u64* __restrict__ in_off,
                     if (lower) cand = ip + (31 - __clz(lower));      // nearest earlier lane
                     ok = cand < pos && ldg_u32_unaligned(src + cand) == v;
                 }
-                __syncwarp();
-                if (valid && (peers >> lane) == 1u) tab[h] = (u16)(pos - seg);   // last writer wins
-                __syncwarp();
                 const unsigned hits = __ballot_sync(FULL, ok);
+                // Insert only positions up to the match start (all 32 on a miss): a position that
+                // will be probed again later must not find itself in the table.
+                const int first = hits ? __ffs(hits) - 1 : 31;
+                const unsigned upto = peers & (0xFFFFFFFFu >> (31 - first));
+                __syncwarp();
+                if (valid && (int)lane <= first && (upto >> lane) == 1u) tab[h] = (u16)(pos - seg);   // last writer wins
+                __syncwarp();
                 if (!hits) { ip += 32; continue; }
-                const int first = __ffs(hits) - 1;
                 u32 mpos = ip + first;
                 u32 mcand = __shfl_sync(FULL, cand, first);
                 while (mpos > anchor && mcand > seg && __ldg(src + mpos - 1) == __ldg(src + mcand - 1)) { mpos--; mcand--; }
@@ -99,6 +102,9 @@ compress_v0_kernel(const u8* __restrict__ in, const u64* __restrict__ in_off,
                 }
                 op = v0_emit_sequence(dst, op, src + anchor, mpos - anchor, mpos - mcand, mlen, lane);
                 ip = anchor = mpos + mlen;
+                if (lane == 0 && ip - 2 >= seg && ip <= mfl)               // lz4/lz4.c:1146 insert ip-2
+                    tab[hash13(ldg_u32_unaligned(src + ip - 2))] = (u16)(ip - 2 - seg);
+                __syncwarp();
             }
         }
     }

@@ -78,6 +78,11 @@ struct lz4b200_ctx {
     int kernel_gen = 1;                 // 0 = warp-per-chunk baseline, 1 = tiled CTA kernels
     cudaStream_t stream = nullptr;      // used by the host-buffer entry points
     uint64_t launches = 0;
+    // optional per-launch timing of the dominant (codec) kernel: event pairs on the launching stream
+    bool timing = false;
+    static constexpr int MAX_TIMED = 256;
+    cudaEvent_t ev0[MAX_TIMED] = {}, ev1[MAX_TIMED] = {};
+    int n_timed = 0;
     // device-resident scratch shared by both directions
     DevBuf usz, csz, uoff, coff;        // u64[n_chunks]
     DevBuf scalars;                     // [0] total (u64), [1] bad chunks (u32), [2] work ticket (u32)
@@ -89,6 +94,20 @@ struct lz4b200_ctx {
 };
 
 namespace {
+
+void time_begin(lz4b200_ctx* c, cudaStream_t st)
+{
+    if (!c->timing || c->n_timed >= lz4b200_ctx::MAX_TIMED) return;
+    int i = c->n_timed;
+    if (!c->ev0[i]) { cudaEventCreate(&c->ev0[i]); cudaEventCreate(&c->ev1[i]); }
+    cudaEventRecord(c->ev0[i], st);
+}
+
+void time_end(lz4b200_ctx* c, cudaStream_t st)
+{
+    if (!c->timing || c->n_timed >= lz4b200_ctx::MAX_TIMED) return;
+    cudaEventRecord(c->ev1[c->n_timed++], st);
+}
 
 size_t slot_stride_for(size_t max_chunk)
 {
@@ -116,6 +135,7 @@ int compress_device_impl(lz4b200_ctx* c, const u8* d_in, const u64* d_usz, size_
     scan_sizes_kernel<<<1, SCAN_THREADS, 0, st>>>(in_scan, none, (u64)n);
     c->launches++;
 
+    time_begin(c, st);
     if (c->kernel_gen >= 1 && v1_compress_supported(max_chunk)) {
         CU(v1_launch_compress(d_in, uoff, d_usz, (u8*)c->stage.p, stride, d_csz, (u32)n,
                               (u32*)c->scalars.p + 4, c->sm_count, st));
@@ -131,6 +151,7 @@ int compress_device_impl(lz4b200_ctx* c, const u8* d_in, const u64* d_usz, size_
             d_in, uoff, d_usz, (u8*)c->stage.p, stride, d_csz, (u32)n);
         c->launches++;
     }
+    time_end(c, st);
     ScanJob out_scan{ d_csz, coff, d_total };
     scan_sizes_kernel<<<1, SCAN_THREADS, 0, st>>>(out_scan, none, (u64)n);
     c->launches++;
@@ -159,6 +180,7 @@ int decompress_device_impl(lz4b200_ctx* c, const u8* d_in, const u64* d_csz, con
     ScanJob a{ d_csz, coff, nullptr }, b{ d_usz, uoff, nullptr };
     scan_sizes_kernel<<<2, SCAN_THREADS, 0, st>>>(a, b, (u64)n);
     c->launches++;
+    time_begin(c, st);
     if (c->kernel_gen >= 1 && v1_decompress_supported(max_chunk)) {
         CU(v1_launch_decompress(d_in, coff, d_csz, uoff, d_usz, d_out, (u32*)c->status.p, d_bad, (u32)n,
                                 (u32*)c->scalars.p + 4, c->sm_count, st));
@@ -168,6 +190,7 @@ int decompress_device_impl(lz4b200_ctx* c, const u8* d_in, const u64* d_csz, con
             d_in, coff, d_csz, uoff, d_usz, d_out, (u32*)c->status.p, d_bad, (u32)n);
         c->launches++;
     }
+    time_end(c, st);
     CU(cudaGetLastError());
     return 0;
 }
@@ -238,6 +261,7 @@ void lz4b200_destroy(lz4b200_ctx* c)
     c->usz.release(); c->csz.release(); c->uoff.release(); c->coff.release();
     c->scalars.release(); c->status.release(); c->stage.release();
     c->d_plain.release(); c->d_packed.release(); c->h_sizes.release();
+    for (int i = 0; i < lz4b200_ctx::MAX_TIMED; i++) if (c->ev0[i]) { cudaEventDestroy(c->ev0[i]); cudaEventDestroy(c->ev1[i]); }
     delete c;
 }
 
@@ -250,7 +274,20 @@ int lz4b200_set_option(lz4b200_ctx* c, const char* key, const char* value)
         if (!strcmp(value, "v0")) { c->kernel_gen = 0; return 0; }
         if (!strcmp(value, "v1")) { c->kernel_gen = 1; return 0; }
     }
+    if (!strcmp(key, "timing")) { c->timing = value[0] == '1'; c->n_timed = 0; return 0; }
     return fail(-1, "unknown option %s=%s", key, value);
+}
+
+int lz4b200_kernel_times_ms(lz4b200_ctx* c, float* out_ms, int max_n)
+{
+    if (!c) return fail(-1, "null ctx");
+    int n = std::min(c->n_timed, max_n);
+    for (int i = 0; i < n; i++) {
+        CU(cudaEventSynchronize(c->ev1[i]));
+        CU(cudaEventElapsedTime(&out_ms[i], c->ev0[i], c->ev1[i]));
+    }
+    c->n_timed = 0;
+    return n;
 }
 
 int lz4b200_compress_device(lz4b200_ctx* c, const void* d_in, const uint64_t* d_chunk_sizes, size_t n_chunks,

@@ -1,6 +1,9 @@
 """Quick device-resident timing probe (not the bench): GB/s of uncompressed bytes per kernel generation."""
+import os
 import sys
 import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 import numpy as np
 import torch

@@ -144,5 +144,5 @@ KATS = [
     ("offset-zero", block(0x48, b"abcd", 0, 0, 0x50, b"vwxyz"), 21, None),
     ("truncated", block(0x48, b"abcd", 4), 21, None),
     ("literal-run-270", block(0xF0, 255, 0, bytes(range(256)) + bytes(range(14))), 270, bytes(range(256)) + bytes(range(14))),
-    ("wrong-size", block(0xD0, b"abcdefghijklm"), 14, None),
+    ("wrong-size", block(0xD0, b"abcdefghijklm"), 15, None),
 ]
