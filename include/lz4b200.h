@@ -99,8 +99,13 @@ uint64_t lz4b200_launch_count(const lz4b200_ctx* ctx);
  * order, clears the list and returns how many were written (negative on error). */
 int lz4b200_kernel_times_ms(lz4b200_ctx* ctx, float* out_ms, int max_n);
 
-/* Tunable: which kernel generation to run ("v0" warp-per-chunk baseline, "v1" tiled CTA
- * kernels).  Also "timing" = "0"/"1" (see above).  Returns 0, or -1 for an unknown key or value.
+/* Debug: cumulative per-phase cycle counters of the tiled kernels (enable with option "prof"="1");
+ * copies 16 counters to out16 and clears them. */
+int lz4b200_debug_prof(lz4b200_ctx* ctx, uint64_t* out16);
+
+/* Tunable: which decode kernel generation to run: "kernels" = "v0" (warp per chunk), "v1"
+ * (one CTA per chunk, TMA-staged shared-memory tile, speculative parallel parse), "v2"
+ * (sub-warp teams, default); "team" = "4"/"8"/"16"/"32" lanes per chunk for v2.  Also "timing" = "0"/"1" (see above).  Returns 0, or -1 for an unknown key or value.
  * Default kernels: the fastest verified generation. */
 int lz4b200_set_option(lz4b200_ctx* ctx, const char* key, const char* value);
 

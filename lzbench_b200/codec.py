@@ -51,6 +51,8 @@ def _load() -> C.CDLL:
     L.lz4b200_launch_count.argtypes = [vp]
     L.lz4b200_kernel_times_ms.restype = C.c_int
     L.lz4b200_kernel_times_ms.argtypes = [vp, vp, C.c_int]
+    L.lz4b200_debug_prof.restype = C.c_int
+    L.lz4b200_debug_prof.argtypes = [vp, vp]
     L.lz4b200_set_option.restype = C.c_int
     L.lz4b200_set_option.argtypes = [vp, C.c_char_p, C.c_char_p]
     L.lzbench_lz4_b200_init.restype = vp
@@ -167,6 +169,12 @@ class Lz4B200:
         if n < 0:
             raise RuntimeError(last_error())
         return [float(buf[i]) for i in range(n)]
+
+    def debug_prof(self):
+        buf = (C.c_uint64 * 16)()
+        if lib.lz4b200_debug_prof(self._h, buf) != 0:
+            raise RuntimeError(last_error())
+        return [int(x) for x in buf]
 
     # -- host-buffer batched calls (the reference-facing hot path) -----------------------
     def compress_batch(self, inbuf, chunk_sizes, outbuf=None) -> Tuple[np.ndarray, np.ndarray, int]:

@@ -9,6 +9,8 @@
 #include "common.cuh"
 #include "kernels_v0.cuh"
 #include "kernels_v1.cuh"
+#include "kernels_v2.cuh"
+#include "kernels_c1.cuh"
 #include "staging.cuh"
 
 #include <algorithm>
@@ -75,8 +77,15 @@ struct PinBuf {
 struct lz4b200_ctx {
     int device = 0;
     int sm_count = 148;
-    int kernel_gen = 1;                 // 0 = warp-per-chunk baseline, 1 = tiled CTA kernels
-    cudaStream_t stream = nullptr;      // used by the host-buffer entry points
+    int kernel_gen = 2;                 // decode: 0 = warp per chunk, 1 = CTA tile (TMA), 2 = sub-warp teams
+    int compress_gen = 1;               // compress: 0 = warp per chunk, 1 = CTA per chunk (parallel match finder)
+    int team = 8;                       // lanes per team for decode generation 2
+    int slices = 0;                     // host entry points: number of pipeline slices (0 = automatic)
+    static constexpr int NS = 4;        // compute/H2D streams of the host pipeline
+    static constexpr int MAX_SLICES = 64;
+    cudaStream_t streams[NS] = {};
+    cudaStream_t d2h_stream = nullptr;
+    cudaEvent_t ev_sizes = nullptr, ev_scan[MAX_SLICES] = {}, ev_done[MAX_SLICES] = {};
     uint64_t launches = 0;
     // optional per-launch timing of the dominant (codec) kernel: event pairs on the launching stream
     bool timing = false;
@@ -85,15 +94,29 @@ struct lz4b200_ctx {
     int n_timed = 0;
     // device-resident scratch shared by both directions
     DevBuf usz, csz, uoff, coff;        // u64[n_chunks]
-    DevBuf scalars;                     // [0] total (u64), [1] bad chunks (u32), [2] work ticket (u32)
+    DevBuf scalars;                     // see Scalars below
     DevBuf status;                      // u32[n_chunks]
+    DevBuf prof;                        // u64[16] phase-cycle counters (debug option "prof")
+    bool prof_on = false;
     DevBuf stage;                       // compress: n_chunks slots of slot_stride bytes
     // buffers behind the host entry points
     DevBuf d_plain, d_packed;
-    PinBuf h_sizes;                     // u64[2*n_chunks + 2]
+    PinBuf h_sizes;                     // u64[2*n_chunks + MAX_SLICES + 2]
 };
 
 namespace {
+
+// layout of ctx->scalars (8 KB)
+constexpr size_t SC_TOTAL = 0;          // u64  total compressed size (device entry point without caller buffer)
+constexpr size_t SC_BAD = 8;            // u32  malformed-chunk counter
+constexpr size_t SC_TICKETS = 256;      // u32[MAX_SLICES] work tickets, one per slice
+constexpr size_t SC_RUNNING = 4096;     // u64[MAX_SLICES] running compressed totals after each slice
+constexpr size_t SC_BYTES = 8192;
+
+// per-slice view of the scratch arrays: slices of one host call run concurrently on different streams
+struct Scratch {
+    u64* uoff; u64* coff; u32* status; u8* stage; u32* ticket;
+};
 
 void time_begin(lz4b200_ctx* c, cudaStream_t st)
 {
@@ -115,31 +138,43 @@ size_t slot_stride_for(size_t max_chunk)
     return (b + 15) & ~size_t(15);
 }
 
-// ---- device pipelines -------------------------------------------------------------------
-
-int compress_device_impl(lz4b200_ctx* c, const u8* d_in, const u64* d_usz, size_t n, size_t max_chunk,
-                         u8* d_out, u64* d_csz, u64* d_total, cudaStream_t st)
+int ensure_scratch(lz4b200_ctx* c, size_t n, size_t stage_bytes)
 {
-    if (n == 0) { CU(cudaMemsetAsync(d_total, 0, sizeof(u64), st)); return 0; }
-    if (n > 0x7FFFFFFFull) return fail(-1, "too many chunks");
-    if (max_chunk > 0x7E000000ull) return fail(-1, "chunk larger than LZ4_MAX_INPUT_SIZE");
-    CU(cudaSetDevice(c->device));
-    const size_t stride = slot_stride_for(max_chunk);
     CU(c->uoff.ensure(n * sizeof(u64)));
     CU(c->coff.ensure(n * sizeof(u64)));
-    CU(c->stage.ensure(n * stride));
-    CU(c->scalars.ensure(64));
-    u64* uoff = (u64*)c->uoff.p; u64* coff = (u64*)c->coff.p;
+    CU(c->status.ensure(n * sizeof(u32)));
+    if (stage_bytes) CU(c->stage.ensure(stage_bytes));
+    if (!c->scalars.p) { CU(c->scalars.ensure(SC_BYTES)); CU(cudaMemset(c->scalars.p, 0, SC_BYTES)); }
+    return 0;
+}
 
-    ScanJob in_scan{ d_usz, uoff, nullptr }, none{ nullptr, nullptr, nullptr };
+Scratch scratch_at(lz4b200_ctx* c, size_t first_chunk, size_t stride, int slice)
+{
+    Scratch s;
+    s.uoff = (u64*)c->uoff.p + first_chunk;
+    s.coff = (u64*)c->coff.p + first_chunk;
+    s.status = (u32*)c->status.p + first_chunk;
+    s.stage = c->stage.p ? (u8*)c->stage.p + first_chunk * stride : nullptr;
+    s.ticket = (u32*)((u8*)c->scalars.p + SC_TICKETS) + slice;
+    return s;
+}
+
+// ---- device pipelines (one slice) ---------------------------------------------------------
+// Compress chunks [0, n) of d_in (sizes d_usz) into staging slots, scan the sizes starting at *base
+// (0 if null), compact into d_out at those absolute offsets, write the running total to *d_total.
+int compress_slice(lz4b200_ctx* c, const u8* d_in, const u64* d_usz, size_t n, size_t max_chunk, u8* d_out,
+                   u64* d_csz, const u64* base, u64* d_total, const Scratch& s, cudaStream_t st,
+                   cudaEvent_t wait_before_scan, cudaEvent_t record_after_scan)
+{
+    const size_t stride = slot_stride_for(max_chunk);
+    ScanJob in_scan{ d_usz, s.uoff, nullptr, nullptr }, none{ nullptr, nullptr, nullptr, nullptr };
     scan_sizes_kernel<<<1, SCAN_THREADS, 0, st>>>(in_scan, none, (u64)n);
     c->launches++;
 
     time_begin(c, st);
-    if (c->kernel_gen >= 1 && v1_compress_supported(max_chunk)) {
-        CU(v1_launch_compress(d_in, uoff, d_usz, (u8*)c->stage.p, stride, d_csz, (u32)n,
-                              (u32*)c->scalars.p + 4, c->sm_count, st));
-        c->launches += 2;
+    if (c->compress_gen == 1 && c1_compress_supported(max_chunk)) {
+        CU(c1_launch_compress(d_in, s.uoff, d_usz, s.stage, stride, d_csz, (u32)n, s.ticket, c->sm_count, max_chunk, st));
+        c->launches++;
     } else {
         const size_t smem = (size_t)V0_WARPS * V0_TABLE * sizeof(u16);
         static bool attr_set = false;
@@ -148,50 +183,79 @@ int compress_device_impl(lz4b200_ctx* c, const u8* d_in, const u64* d_usz, size_
             attr_set = true;
         }
         compress_v0_kernel<<<(unsigned)((n + V0_WARPS - 1) / V0_WARPS), V0_WARPS * 32, smem, st>>>(
-            d_in, uoff, d_usz, (u8*)c->stage.p, stride, d_csz, (u32)n);
+            d_in, s.uoff, d_usz, s.stage, stride, d_csz, (u32)n);
         c->launches++;
     }
     time_end(c, st);
-    ScanJob out_scan{ d_csz, coff, d_total };
+    if (wait_before_scan) CU(cudaStreamWaitEvent(st, wait_before_scan, 0));
+    ScanJob out_scan{ d_csz, s.coff, d_total, base };
     scan_sizes_kernel<<<1, SCAN_THREADS, 0, st>>>(out_scan, none, (u64)n);
     c->launches++;
+    if (record_after_scan) CU(cudaEventRecord(record_after_scan, st));
     const unsigned grid = (unsigned)std::min<size_t>(n, (size_t)c->sm_count * 16);
-    compact_kernel<<<grid, COMPACT_THREADS, 0, st>>>((const u8*)c->stage.p, stride, d_in, uoff, d_usz,
-                                                     d_csz, coff, d_out, (u32)n);
+    compact_kernel<<<grid, COMPACT_THREADS, 0, st>>>(s.stage, stride, d_in, s.uoff, d_usz, d_csz, s.coff, d_out, (u32)n);
     c->launches++;
     CU(cudaGetLastError());
     return 0;
 }
 
-int decompress_device_impl(lz4b200_ctx* c, const u8* d_in, const u64* d_csz, const u64* d_usz, size_t n,
-                           size_t max_chunk, u8* d_out, u32* d_bad, cudaStream_t st)
+int decompress_slice(lz4b200_ctx* c, const u8* d_in, const u64* d_csz, const u64* d_usz, size_t n, size_t max_chunk,
+                     u8* d_out, u32* d_bad, const Scratch& s, cudaStream_t st)
 {
-    CU(cudaSetDevice(c->device));
-    CU(c->scalars.ensure(64));
-    if (!d_bad) d_bad = (u32*)c->scalars.p + 2;
-    CU(cudaMemsetAsync(d_bad, 0, sizeof(u32), st));
-    if (n == 0) return 0;
-    if (n > 0x7FFFFFFFull) return fail(-1, "too many chunks");
-    if (max_chunk > 0x7E000000ull) return fail(-1, "chunk larger than LZ4_MAX_INPUT_SIZE");
-    CU(c->uoff.ensure(n * sizeof(u64)));
-    CU(c->coff.ensure(n * sizeof(u64)));
-    CU(c->status.ensure(n * sizeof(u32)));
-    u64* uoff = (u64*)c->uoff.p; u64* coff = (u64*)c->coff.p;
-    ScanJob a{ d_csz, coff, nullptr }, b{ d_usz, uoff, nullptr };
+    ScanJob a{ d_csz, s.coff, nullptr, nullptr }, b{ d_usz, s.uoff, nullptr, nullptr };
     scan_sizes_kernel<<<2, SCAN_THREADS, 0, st>>>(a, b, (u64)n);
     c->launches++;
     time_begin(c, st);
-    if (c->kernel_gen >= 1 && v1_decompress_supported(max_chunk)) {
-        CU(v1_launch_decompress(d_in, coff, d_csz, uoff, d_usz, d_out, (u32*)c->status.p, d_bad, (u32)n,
-                                (u32*)c->scalars.p + 4, c->sm_count, st));
-        c->launches += 2;
+    if (c->kernel_gen == 2) {
+        CU(v2_launch_decompress(c->team, d_in, s.coff, d_csz, s.uoff, d_usz, d_out, s.status, d_bad, (u32)n,
+                                s.ticket, c->sm_count, st));
+        c->launches += 1;
+    } else if (c->kernel_gen == 1 && v1_decompress_supported(max_chunk)) {
+        CU(v1_launch_decompress(d_in, s.coff, d_csz, s.uoff, d_usz, d_out, s.status, d_bad, (u32)n, s.ticket,
+                                c->prof_on ? (u64*)c->prof.p : nullptr, c->sm_count, max_chunk, st));
+        c->launches += 1;
     } else {
         decompress_v0_kernel<<<(unsigned)((n + V0_WARPS - 1) / V0_WARPS), V0_WARPS * 32, 0, st>>>(
-            d_in, coff, d_csz, uoff, d_usz, d_out, (u32*)c->status.p, d_bad, (u32)n);
+            d_in, s.coff, d_csz, s.uoff, d_usz, d_out, s.status, d_bad, (u32)n);
         c->launches++;
     }
     time_end(c, st);
     CU(cudaGetLastError());
+    return 0;
+}
+
+int check_batch(size_t n, size_t max_chunk)
+{
+    if (n > 0x7FFFFFFFull) return fail(-1, "too many chunks");
+    if (max_chunk > 0x7E000000ull) return fail(-1, "chunk larger than LZ4_MAX_INPUT_SIZE");
+    return 0;
+}
+
+// Cut chunks [0,n) into K contiguous slices of roughly equal uncompressed size; first[k] = first chunk of slice k.
+int plan_slices(const lz4b200_ctx* c, const size_t* chunk_sizes, size_t n, size_t total, size_t* first /* K+1 */)
+{
+    int K = c->slices;
+    if (K <= 0) K = total >= (256u << 20) ? 4 : (total >= (32u << 20) ? 2 : 1);
+    if (K > lz4b200_ctx::MAX_SLICES) K = lz4b200_ctx::MAX_SLICES;
+    if ((size_t)K > n) K = (int)n;
+    size_t acc = 0, k = 1;
+    first[0] = 0;
+    for (size_t i = 0; i < n && k < (size_t)K; i++) {
+        acc += chunk_sizes[i];
+        if (acc >= total * k / K && i + 1 < n) first[k++] = i + 1;
+    }
+    K = (int)k;
+    first[K] = n;
+    return K;
+}
+
+int ensure_events(lz4b200_ctx* c, int K)
+{
+    if (!c->ev_sizes) CU(cudaEventCreateWithFlags(&c->ev_sizes, cudaEventDisableTiming));
+    for (int k = 0; k < K; k++) {
+        if (!c->ev_scan[k]) CU(cudaEventCreateWithFlags(&c->ev_scan[k], cudaEventDisableTiming));
+        if (!c->ev_done[k]) CU(cudaEventCreateWithFlags(&c->ev_done[k], cudaEventDisableTiming));
+    }
     return 0;
 }
 
@@ -235,20 +299,26 @@ int lz4b200_create(int device, size_t max_total_bytes, size_t max_chunk_bytes, l
     c->device = device;
     c->sm_count = prop.multiProcessorCount;
     const char* gen = getenv("LZ4B200_KERNELS");
-    if (gen && !strcmp(gen, "v0")) c->kernel_gen = 0;
-    cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
-    if (e != cudaSuccess) { delete c; return fail(-2, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
+    if (gen && !strcmp(gen, "v0")) { c->kernel_gen = 0; c->compress_gen = 0; }
+    if (gen && !strcmp(gen, "v1")) c->kernel_gen = 1;
+    for (int i = 0; i < lz4b200_ctx::NS; i++) {
+        cudaError_t e = cudaStreamCreateWithFlags(&c->streams[i], cudaStreamNonBlocking);
+        if (e != cudaSuccess) { lz4b200_destroy(c); return fail(-2, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
+    }
+    if (cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking) != cudaSuccess) {
+        lz4b200_destroy(c); return fail(-2, "cudaStreamCreate failed");
+    }
     if (max_total_bytes && max_chunk_bytes) {
         size_t n = (max_total_bytes + max_chunk_bytes - 1) / max_chunk_bytes;
         // best-effort pre-sizing; growth on demand covers the rest
-        c->d_plain.ensure(max_total_bytes);
-        c->d_packed.ensure(max_total_bytes + max_total_bytes / 255 + 16 * n);
+        c->d_plain.ensure(max_total_bytes + 16);
+        c->d_packed.ensure(max_total_bytes + max_total_bytes / 255 + 16 * n + 16);
         c->stage.ensure(n * slot_stride_for(max_chunk_bytes));
         c->usz.ensure(n * 8); c->csz.ensure(n * 8); c->uoff.ensure(n * 8); c->coff.ensure(n * 8);
         c->status.ensure(n * 4);
-        c->h_sizes.ensure((2 * n + 2) * 8);
+        c->h_sizes.ensure((2 * n + lz4b200_ctx::MAX_SLICES + 2) * 8);
     }
-    c->scalars.ensure(64);
+    if (ensure_scratch(c, 1, 0) != 0) { lz4b200_destroy(c); return -2; }
     *out = c;
     return 0;
 }
@@ -257,10 +327,17 @@ void lz4b200_destroy(lz4b200_ctx* c)
 {
     if (!c) return;
     cudaSetDevice(c->device);
-    if (c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
+    cudaDeviceSynchronize();
+    for (int i = 0; i < lz4b200_ctx::NS; i++) if (c->streams[i]) cudaStreamDestroy(c->streams[i]);
+    if (c->d2h_stream) cudaStreamDestroy(c->d2h_stream);
+    if (c->ev_sizes) cudaEventDestroy(c->ev_sizes);
+    for (int i = 0; i < lz4b200_ctx::MAX_SLICES; i++) {
+        if (c->ev_scan[i]) cudaEventDestroy(c->ev_scan[i]);
+        if (c->ev_done[i]) cudaEventDestroy(c->ev_done[i]);
+    }
     c->usz.release(); c->csz.release(); c->uoff.release(); c->coff.release();
     c->scalars.release(); c->status.release(); c->stage.release();
-    c->d_plain.release(); c->d_packed.release(); c->h_sizes.release();
+    c->d_plain.release(); c->d_packed.release(); c->h_sizes.release(); c->prof.release();
     for (int i = 0; i < lz4b200_ctx::MAX_TIMED; i++) if (c->ev0[i]) { cudaEventDestroy(c->ev0[i]); cudaEventDestroy(c->ev1[i]); }
     delete c;
 }
@@ -270,12 +347,39 @@ uint64_t lz4b200_launch_count(const lz4b200_ctx* c) { return c ? c->launches : 0
 int lz4b200_set_option(lz4b200_ctx* c, const char* key, const char* value)
 {
     if (!c || !key || !value) return -1;
-    if (!strcmp(key, "kernels")) {
-        if (!strcmp(value, "v0")) { c->kernel_gen = 0; return 0; }
-        if (!strcmp(value, "v1")) { c->kernel_gen = 1; return 0; }
+    if (!strcmp(key, "kernels")) {          // decode generation (and v0 also selects the v0 compressor)
+        if (!strcmp(value, "v0")) { c->kernel_gen = 0; c->compress_gen = 0; return 0; }
+        if (!strcmp(value, "v1")) { c->kernel_gen = 1; c->compress_gen = 1; return 0; }
+        if (!strcmp(value, "v2")) { c->kernel_gen = 2; c->compress_gen = 1; return 0; }
+    }
+    if (!strcmp(key, "compress")) {
+        if (!strcmp(value, "v0")) { c->compress_gen = 0; return 0; }
+        if (!strcmp(value, "v1")) { c->compress_gen = 1; return 0; }
+    }
+    if (!strcmp(key, "team")) {
+        int t = atoi(value);
+        if (t == 4 || t == 8 || t == 16 || t == 32) { c->team = t; return 0; }
+    }
+    if (!strcmp(key, "slices")) {
+        int k = atoi(value);
+        if (k >= 0 && k <= lz4b200_ctx::MAX_SLICES) { c->slices = k; return 0; }
+    }
+    if (!strcmp(key, "prof")) {
+        c->prof_on = value[0] == '1';
+        if (c->prof_on) { if (c->prof.ensure(128) != cudaSuccess) return fail(-2, "prof alloc"); cudaMemset(c->prof.p, 0, 128); }
+        return 0;
     }
     if (!strcmp(key, "timing")) { c->timing = value[0] == '1'; c->n_timed = 0; return 0; }
     return fail(-1, "unknown option %s=%s", key, value);
+}
+
+int lz4b200_debug_prof(lz4b200_ctx* c, uint64_t* out16)
+{
+    if (!c || !c->prof.p) return fail(-1, "prof not enabled");
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemcpy(out16, c->prof.p, 128, cudaMemcpyDeviceToHost));
+    CU(cudaMemset(c->prof.p, 0, 128));
+    return 0;
 }
 
 int lz4b200_kernel_times_ms(lz4b200_ctx* c, float* out_ms, int max_n)
@@ -290,24 +394,43 @@ int lz4b200_kernel_times_ms(lz4b200_ctx* c, float* out_ms, int max_n)
     return n;
 }
 
-int lz4b200_compress_device(lz4b200_ctx* c, const void* d_in, const uint64_t* d_chunk_sizes, size_t n_chunks,
-                            size_t max_chunk_bytes, void* d_out, uint64_t* d_compr_sizes,
+int lz4b200_compress_device(lz4b200_ctx* c, const void* d_in, const uint64_t* d_chunk_sizes, size_t n,
+                            size_t max_chunk, void* d_out, uint64_t* d_compr_sizes,
                             uint64_t* d_total_out, void* stream)
 {
     if (!c) return fail(-1, "null ctx");
-    return compress_device_impl(c, (const u8*)d_in, (const u64*)d_chunk_sizes, n_chunks, max_chunk_bytes,
-                                (u8*)d_out, (u64*)d_compr_sizes, (u64*)d_total_out, (cudaStream_t)stream);
+    cudaStream_t st = (cudaStream_t)stream;
+    CU(cudaSetDevice(c->device));
+    if (n == 0) { if (d_total_out) CU(cudaMemsetAsync(d_total_out, 0, sizeof(u64), st)); return 0; }
+    if (int rc = check_batch(n, max_chunk)) return rc;
+    if (int rc = ensure_scratch(c, n, n * slot_stride_for(max_chunk))) return rc;
+    u64* total = d_total_out ? (u64*)d_total_out : (u64*)((u8*)c->scalars.p + SC_TOTAL);
+    return compress_slice(c, (const u8*)d_in, (const u64*)d_chunk_sizes, n, max_chunk, (u8*)d_out,
+                          (u64*)d_compr_sizes, nullptr, total, scratch_at(c, 0, slot_stride_for(max_chunk), 0), st,
+                          nullptr, nullptr);
 }
 
 int lz4b200_decompress_device(lz4b200_ctx* c, const void* d_in, const uint64_t* d_compr_sizes,
-                              const uint64_t* d_chunk_sizes, size_t n_chunks, size_t max_chunk_bytes,
+                              const uint64_t* d_chunk_sizes, size_t n, size_t max_chunk,
                               void* d_out, uint32_t* d_bad_chunks, void* stream)
 {
     if (!c) return fail(-1, "null ctx");
-    return decompress_device_impl(c, (const u8*)d_in, (const u64*)d_compr_sizes, (const u64*)d_chunk_sizes,
-                                  n_chunks, max_chunk_bytes, (u8*)d_out, d_bad_chunks, (cudaStream_t)stream);
+    cudaStream_t st = (cudaStream_t)stream;
+    CU(cudaSetDevice(c->device));
+    if (int rc = ensure_scratch(c, n ? n : 1, 0)) return rc;
+    u32* bad = d_bad_chunks ? d_bad_chunks : (u32*)((u8*)c->scalars.p + SC_BAD);
+    CU(cudaMemsetAsync(bad, 0, sizeof(u32), st));
+    if (n == 0) return 0;
+    if (int rc = check_batch(n, max_chunk)) return rc;
+    return decompress_slice(c, (const u8*)d_in, (const u64*)d_compr_sizes, (const u64*)d_chunk_sizes, n, max_chunk,
+                            (u8*)d_out, bad, scratch_at(c, 0, 0, 0), st);
 }
 
+// Host-buffer compress: slices of the chunk list flow through H2D -> kernels -> D2H on NS streams so the
+// PCIe copies of one slice overlap the kernels of another.  The compacted position of a slice depends on
+// the compressed size of the slices before it, which exists only on the device: the output scan of slice
+// k starts from the running total slice k-1 left in device memory (event-ordered), and the host learns
+// the totals one slice behind to place the D2H copies.
 int64_t lz4b200_compress_batch(lz4b200_ctx* c, const char* in, const size_t* chunk_sizes, size_t n,
                                char* out, size_t out_capacity, size_t* compr_sizes)
 {
@@ -316,29 +439,57 @@ int64_t lz4b200_compress_batch(lz4b200_ctx* c, const char* in, const size_t* chu
     if (!in || !chunk_sizes || !out || !compr_sizes) return fail(-1, "null argument");
     CU(cudaSetDevice(c->device));
     size_t total = 0, max_chunk = 0;
-    CU(c->h_sizes.ensure((2 * n + 2) * sizeof(u64)));
+    CU(c->h_sizes.ensure((2 * n + lz4b200_ctx::MAX_SLICES + 2) * sizeof(u64)));
     u64* h = (u64*)c->h_sizes.p;
+    u64* h_tot = h + 2 * n;
     for (size_t i = 0; i < n; i++) { h[i] = chunk_sizes[i]; total += chunk_sizes[i]; max_chunk = std::max(max_chunk, chunk_sizes[i]); }
-    if (max_chunk > 0x7E000000ull) return fail(-1, "chunk larger than LZ4_MAX_INPUT_SIZE");
+    if (int rc = check_batch(n, max_chunk)) return rc;
+    const size_t stride = slot_stride_for(max_chunk);
     CU(c->usz.ensure(n * 8)); CU(c->csz.ensure(n * 8));
     CU(c->d_plain.ensure(total + 16));
     CU(c->d_packed.ensure(total + total / 255 + 16 * n + 16));
-    CU(c->scalars.ensure(64));
-    cudaStream_t st = c->stream;
-    CU(cudaMemcpyAsync(c->usz.p, h, n * 8, cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(c->d_plain.p, in, total, cudaMemcpyHostToDevice, st));
-    int rc = compress_device_impl(c, (const u8*)c->d_plain.p, (const u64*)c->usz.p, n, max_chunk,
-                                  (u8*)c->d_packed.p, (u64*)c->csz.p, (u64*)c->scalars.p, st);
-    if (rc) return rc;
-    CU(cudaMemcpyAsync(h + n, c->csz.p, n * 8, cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(h + 2 * n, c->scalars.p, 8, cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
-    const u64 ctotal = h[2 * n];
-    if (ctotal > out_capacity) { fail(0, "compressed size %llu exceeds output capacity %zu", ctotal, out_capacity); return 0; }
-    CU(cudaMemcpyAsync(out, c->d_packed.p, ctotal, cudaMemcpyDeviceToHost, st));
+    if (int rc = ensure_scratch(c, n, n * stride)) return rc;
+    size_t first[lz4b200_ctx::MAX_SLICES + 1];
+    const int K = plan_slices(c, chunk_sizes, n, total, first);
+    if (int rc = ensure_events(c, K)) return rc;
+
+    u64* running = (u64*)((u8*)c->scalars.p + SC_RUNNING);
+    CU(cudaMemcpyAsync(c->usz.p, h, n * 8, cudaMemcpyHostToDevice, c->streams[0]));
+    CU(cudaEventRecord(c->ev_sizes, c->streams[0]));
+    size_t in_off = 0;
+    for (int k = 0; k < K; k++) {
+        cudaStream_t st = c->streams[k % lz4b200_ctx::NS];
+        const size_t f = first[k], m = first[k + 1] - first[k];
+        size_t bytes = 0;
+        for (size_t i = f; i < f + m; i++) bytes += chunk_sizes[i];
+        CU(cudaStreamWaitEvent(st, c->ev_sizes, 0));
+        CU(cudaMemcpyAsync((u8*)c->d_plain.p + in_off, in + in_off, bytes, cudaMemcpyHostToDevice, st));
+        int rc = compress_slice(c, (const u8*)c->d_plain.p + in_off, (const u64*)c->usz.p + f, m, max_chunk,
+                                (u8*)c->d_packed.p, (u64*)c->csz.p + f, k ? running + (k - 1) : nullptr, running + k,
+                                scratch_at(c, f, stride, k), st, k ? c->ev_scan[k - 1] : nullptr, c->ev_scan[k]);
+        if (rc) { cudaDeviceSynchronize(); return rc; }
+        CU(cudaMemcpyAsync(h_tot + k, running + k, 8, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(h + n + f, (u64*)c->csz.p + f, m * 8, cudaMemcpyDeviceToHost, st));
+        CU(cudaEventRecord(c->ev_done[k], st));
+        in_off += bytes;
+    }
+    u64 base = 0;
+    bool overflow = false;
+    for (int k = 0; k < K; k++) {
+        CU(cudaEventSynchronize(c->ev_done[k]));
+        const u64 end = h_tot[k];
+        if (end > out_capacity) { overflow = true; break; }
+        CU(cudaMemcpyAsync(out + base, (u8*)c->d_packed.p + base, end - base, cudaMemcpyDeviceToHost, c->d2h_stream));
+        base = end;
+    }
+    if (overflow) {
+        CU(cudaDeviceSynchronize());
+        fail(0, "compressed image exceeds output capacity %zu", out_capacity);
+        return 0;                                        // _lzbench/lzbench.cpp:286
+    }
+    CU(cudaStreamSynchronize(c->d2h_stream));
     for (size_t i = 0; i < n; i++) compr_sizes[i] = (size_t)h[n + i];
-    CU(cudaStreamSynchronize(st));
-    return (int64_t)ctotal;
+    return (int64_t)base;
 }
 
 int64_t lz4b200_decompress_batch(lz4b200_ctx* c, const char* in, const size_t* compr_sizes,
@@ -349,31 +500,47 @@ int64_t lz4b200_decompress_batch(lz4b200_ctx* c, const char* in, const size_t* c
     if (!in || !chunk_sizes || !out || !compr_sizes) return fail(-1, "null argument");
     CU(cudaSetDevice(c->device));
     size_t total = 0, ctotal = 0, max_chunk = 0;
-    CU(c->h_sizes.ensure((2 * n + 2) * sizeof(u64)));
+    CU(c->h_sizes.ensure((2 * n + lz4b200_ctx::MAX_SLICES + 2) * sizeof(u64)));
     u64* h = (u64*)c->h_sizes.p;
     for (size_t i = 0; i < n; i++) {
         h[i] = chunk_sizes[i]; h[n + i] = compr_sizes[i];
         total += chunk_sizes[i]; ctotal += compr_sizes[i];
         max_chunk = std::max(max_chunk, chunk_sizes[i]);
     }
-    if (max_chunk > 0x7E000000ull) return fail(-1, "chunk larger than LZ4_MAX_INPUT_SIZE");
+    if (int rc = check_batch(n, max_chunk)) return rc;
     CU(c->usz.ensure(n * 8)); CU(c->csz.ensure(n * 8));
     CU(c->d_plain.ensure(total + 16));
     CU(c->d_packed.ensure(ctotal + 16));
-    CU(c->scalars.ensure(64));
-    cudaStream_t st = c->stream;
-    CU(cudaMemcpyAsync(c->usz.p, h, n * 8, cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(c->csz.p, h + n, n * 8, cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(c->d_packed.p, in, ctotal, cudaMemcpyHostToDevice, st));
-    u32* d_bad = (u32*)c->scalars.p + 2;
-    int rc = decompress_device_impl(c, (const u8*)c->d_packed.p, (const u64*)c->csz.p, (const u64*)c->usz.p, n,
-                                    max_chunk, (u8*)c->d_plain.p, d_bad, st);
-    if (rc) return rc;
-    CU(cudaMemcpyAsync(out, c->d_plain.p, total, cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(h + 2 * n, d_bad, 4, cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
-    const u32 bad = *(const u32*)(h + 2 * n);
-    if (bad) { fail(-1, "%u malformed chunk(s)", bad); return -(int64_t)bad; }
+    if (int rc = ensure_scratch(c, n, 0)) return rc;
+    size_t first[lz4b200_ctx::MAX_SLICES + 1];
+    const int K = plan_slices(c, chunk_sizes, n, total, first);
+    if (int rc = ensure_events(c, K)) return rc;
+
+    u32* d_bad = (u32*)((u8*)c->scalars.p + SC_BAD);
+    CU(cudaMemsetAsync(d_bad, 0, 4, c->streams[0]));
+    CU(cudaMemcpyAsync(c->usz.p, h, n * 8, cudaMemcpyHostToDevice, c->streams[0]));
+    CU(cudaMemcpyAsync(c->csz.p, h + n, n * 8, cudaMemcpyHostToDevice, c->streams[0]));
+    CU(cudaEventRecord(c->ev_sizes, c->streams[0]));
+    size_t uoff = 0, coff = 0;
+    for (int k = 0; k < K; k++) {
+        cudaStream_t st = c->streams[k % lz4b200_ctx::NS];
+        const size_t f = first[k], m = first[k + 1] - first[k];
+        size_t ub = 0, cb = 0;
+        for (size_t i = f; i < f + m; i++) { ub += chunk_sizes[i]; cb += compr_sizes[i]; }
+        CU(cudaStreamWaitEvent(st, c->ev_sizes, 0));
+        CU(cudaMemcpyAsync((u8*)c->d_packed.p + coff, in + coff, cb, cudaMemcpyHostToDevice, st));
+        int rc = decompress_slice(c, (const u8*)c->d_packed.p + coff, (const u64*)c->csz.p + f, (const u64*)c->usz.p + f,
+                                  m, max_chunk, (u8*)c->d_plain.p + uoff, d_bad, scratch_at(c, f, 0, k), st);
+        if (rc) { cudaDeviceSynchronize(); return rc; }
+        CU(cudaEventRecord(c->ev_done[k], st));
+        CU(cudaStreamWaitEvent(c->d2h_stream, c->ev_done[k], 0));
+        CU(cudaMemcpyAsync(out + uoff, (u8*)c->d_plain.p + uoff, ub, cudaMemcpyDeviceToHost, c->d2h_stream));
+        uoff += ub; coff += cb;
+    }
+    u32* h_bad = (u32*)(h + 2 * n);
+    CU(cudaMemcpyAsync(h_bad, d_bad, 4, cudaMemcpyDeviceToHost, c->d2h_stream));
+    CU(cudaStreamSynchronize(c->d2h_stream));
+    if (*h_bad) { fail(-1, "%u malformed chunk(s)", *h_bad); return -(int64_t)*h_bad; }
     return (int64_t)total;
 }
 

@@ -30,7 +30,10 @@ for kind in kinds:
     d_bad = torch.zeros(1, dtype=torch.int32, device="cuda")
     s = torch.cuda.current_stream().cuda_stream
     for gen in gens:
-        ctx.set_option("kernels", gen)
+        if gen.startswith("v2t"):
+            ctx.set_option("kernels", "v2"); ctx.set_option("team", gen[3:])
+        else:
+            ctx.set_option("kernels", gen)
         def comp(): ctx.compress_device(d_in, d_cs, n_chunks, chunk, d_out, d_compr, d_total, s)
         def deco(): ctx.decompress_device(d_out, d_compr, d_cs, n_chunks, chunk, d_back, d_bad, s)
         res = {}
@@ -42,6 +45,11 @@ for kind in kinds:
                 e0.record(); fn(); e1.record(); torch.cuda.synchronize()
                 ts.append(e0.elapsed_time(e1))
             res[name] = min(ts)
+        if gen == "v1" and os.environ.get("PROF"):
+            ctx.set_option("prof", "1"); deco(); pr = ctx.debug_prof(); ctx.set_option("prof", "0")
+            tot = sum(pr[:8]) or 1
+            print("   decode phases [ticket,load,parse,scan,literals,matches,(coop),store] %:",
+                  [round(100 * x / tot, 1) for x in pr[:7]], "cycles/chunk", tot // n_chunks, flush=True)
         total = int(d_total.item())
         ok = bool(torch.equal(d_back, d_in)) and int(d_bad.item()) == 0
         print(f"{kind} {n>>20}MiB chunk={chunk} {gen}: ratio={100*total/n:.2f}% "
