@@ -124,9 +124,10 @@ __device__ __forceinline__ u32 c1_block_excl(u32 v, u32* warp_scratch, u32& tota
     return excl;
 }
 
+template <int MODE>
 __global__ void __launch_bounds__(C1_THREADS, 2)
 compress_c1_kernel(const u8* __restrict__ in, const u64* __restrict__ in_off, const u64* __restrict__ usz,
-                   u8* __restrict__ stage, u64 slot_stride, u64* __restrict__ csz, u32 n_chunks, u32* ticket)
+                   u8* __restrict__ stage, u64 slot_stride, u64* __restrict__ csz, u32 n_chunks, u32* ticket, u64* prof)
 {
     extern __shared__ __align__(128) u8 smem[];
     u8* const s_in_raw = smem + C1Smem::OFF_IN;
@@ -149,6 +150,9 @@ compress_c1_kernel(const u8* __restrict__ in, const u64* __restrict__ in_off, co
     u32 phase = 0;
     if (tid == 0) mbar_init(s_bar, 1);
     __syncthreads();
+    long long t_prev = prof ? clock64() : 0;
+    u64 t_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#define C1_TICK(k) do { if (prof && tid == 0) { long long t_ = clock64(); t_acc[k] += (u64)(t_ - t_prev); t_prev = t_; } } while (0)
 
     for (;;) {
         if (tid == 0) s_misc[0] = atomicAdd(ticket, 1u);
@@ -179,6 +183,7 @@ compress_c1_kernel(const u8* __restrict__ in, const u64* __restrict__ in_off, co
             if (bulk) { mbar_wait(s_bar, phase); phase ^= 1; }
         }
         __syncthreads();
+        C1_TICK(0);
 
         u32 cur = 0;                                    // chain state: end of the last match (= literal anchor)
         u32 op = 0;                                     // bytes emitted so far
@@ -192,13 +197,29 @@ compress_c1_kernel(const u8* __restrict__ in, const u64* __restrict__ in_off, co
                     const bool valid = p <= mfl;
                     u32 v = 0, h = 0x10000u + lane, cand = 0;
                     if (valid) { v = c1_rd32(s_in + p); h = hash13(v); cand = s_tab[h]; }
-                    const unsigned peers = __match_any_sync(FULL, h);
-                    const unsigned lower = peers & ((1u << lane) - 1u);
                     bool ok = false;
-                    if (valid) {
-                        if (lower) cand = p - (lane - (31 - __clz(lower)));
-                        ok = cand < p && c1_rd32(s_in + cand) == v;
-                        if ((peers >> lane) == 1u) s_tab[h] = (u16)p;          // highest lane of the group
+                    if (MODE == 0) {                    // exact nearest earlier lane with the same hash
+                        const unsigned peers = __match_any_sync(FULL, h);
+                        const unsigned lower = peers & ((1u << lane) - 1u);
+                        if (valid) {
+                            if (lower) cand = p - (lane - (31 - __clz(lower)));
+                            ok = cand < p && c1_rd32(s_in + cand) == v;
+                            if ((peers >> lane) == 1u) s_tab[h] = (u16)p;      // highest lane of the group
+                        }
+                    } else {
+                        if (MODE == 1) {                // short periods inside the warp: same 4 bytes d lanes earlier
+                            u32 d_hit = 0;
+                            #pragma unroll
+                            for (u32 d : {16u, 8u, 4u, 3u, 2u, 1u}) {
+                                const u32 y = __shfl_up_sync(FULL, v, d);
+                                if (lane >= d && y == v) d_hit = d;
+                            }
+                            if (valid && d_hit) cand = p - d_hit;
+                        }
+                        if (valid) {
+                            ok = cand < p && c1_rd32(s_in + cand) == v;
+                            s_tab[h] = (u16)p;                                  // racing lanes: any winner is a valid candidate
+                        }
                     }
                     s_moff[b + tid] = ok ? (u16)(p - cand) : (u16)0;
                     const unsigned hit = __ballot_sync(FULL, ok);
@@ -206,13 +227,16 @@ compress_c1_kernel(const u8* __restrict__ in, const u64* __restrict__ in_off, co
                     __syncthreads();
                 }
 
+                C1_TICK(1);
                 // ---- P: greedy parse by speculative windows ----
                 const u32 wstart = t0 + tid * C1_WP, wend = wstart + C1_WP;
                 const u32 wbits = (s_bits[tid >> 1] >> ((tid & 1) * 16)) & 0xFFFFu;
                 u32 entry = cur, nrec = 0, exitv = cur;
                 bool capped = false;
                 bool need_walk = true;
+                u32 round_count = 0;
                 for (u32 round = 0;; round++) {
+                    round_count++;
                     if (need_walk) {
                         u32 pos = entry > wstart ? entry : wstart;
                         nrec = 0; capped = false; exitv = entry;
@@ -301,6 +325,8 @@ compress_c1_kernel(const u8* __restrict__ in, const u64* __restrict__ in_off, co
                     }
                 }
 
+                C1_TICK(2);
+                if (prof && tid == 0) t_acc[5] += round_count;
                 // ---- E: emit the tile's sequences ----
                 // pass 1: backward catch-up (lz4/lz4.c:1019) and encoded size per window
                 u32 enc = 0;
@@ -352,6 +378,7 @@ compress_c1_kernel(const u8* __restrict__ in, const u64* __restrict__ in_off, co
                 }
                 op += tile_bytes;
                 __syncthreads();
+                C1_TICK(3);
             }
         }
         // ---- last literals (lz4/lz4.c:1204-1231) ----
@@ -368,17 +395,22 @@ compress_c1_kernel(const u8* __restrict__ in, const u64* __restrict__ in_off, co
         }
         if (tid == 0) csz[chunk] = op;
         __syncthreads();
+        C1_TICK(4);
     }
+    if (prof && tid == 0)
+        for (int k = 0; k < 8; k++) atomicAdd(reinterpret_cast<unsigned long long*>(prof) + 8 + k, (unsigned long long)t_acc[k]);
+#undef C1_TICK
 }
 
 inline bool c1_compress_supported(size_t max_chunk) { return max_chunk <= C1_CHUNK_MAX; }
 
-inline cudaError_t c1_launch_compress(const u8* in, const u64* in_off, const u64* usz, u8* stage, u64 stride, u64* csz,
-                                      u32 n, u32* ticket, int sm_count, size_t, cudaStream_t st)
+template <int MODE>
+inline cudaError_t c1_launch_mode(const u8* in, const u64* in_off, const u64* usz, u8* stage, u64 stride, u64* csz,
+                                      u32 n, u32* ticket, u64* prof, int sm_count, size_t, cudaStream_t st)
 {
     static bool attr = false;
     if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(compress_c1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t e = cudaFuncSetAttribute(compress_c1_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)C1Smem::BYTES);
         if (e != cudaSuccess) return e;
         attr = true;
@@ -387,8 +419,20 @@ inline cudaError_t c1_launch_compress(const u8* in, const u64* in_off, const u64
     if (grid > n) grid = n;
     cudaError_t e = cudaMemsetAsync(ticket, 0, sizeof(u32), st);
     if (e != cudaSuccess) return e;
-    compress_c1_kernel<<<grid, C1_THREADS, C1Smem::BYTES, st>>>(in, in_off, usz, stage, stride, csz, n, ticket);
+    compress_c1_kernel<MODE><<<grid, C1_THREADS, C1Smem::BYTES, st>>>(in, in_off, usz, stage, stride, csz, n, ticket, prof);
     return cudaGetLastError();
+}
+
+inline int& c1_mode() { static int m = 1; return m; }   // 0 match_any, 1 shuffle distances (default), 2 table only
+
+inline cudaError_t c1_launch_compress(const u8* in, const u64* in_off, const u64* usz, u8* stage, u64 stride, u64* csz,
+                                      u32 n, u32* ticket, u64* prof, int sm_count, size_t mc, cudaStream_t st)
+{
+    switch (c1_mode()) {
+    case 1:  return c1_launch_mode<1>(in, in_off, usz, stage, stride, csz, n, ticket, prof, sm_count, mc, st);
+    case 2:  return c1_launch_mode<2>(in, in_off, usz, stage, stride, csz, n, ticket, prof, sm_count, mc, st);
+    default: return c1_launch_mode<0>(in, in_off, usz, stage, stride, csz, n, ticket, prof, sm_count, mc, st);
+    }
 }
 
 }  // namespace lz4b200

@@ -173,7 +173,8 @@ int compress_slice(lz4b200_ctx* c, const u8* d_in, const u64* d_usz, size_t n, s
 
     time_begin(c, st);
     if (c->compress_gen == 1 && c1_compress_supported(max_chunk)) {
-        CU(c1_launch_compress(d_in, s.uoff, d_usz, s.stage, stride, d_csz, (u32)n, s.ticket, c->sm_count, max_chunk, st));
+        CU(c1_launch_compress(d_in, s.uoff, d_usz, s.stage, stride, d_csz, (u32)n, s.ticket,
+                              c->prof_on ? (u64*)c->prof.p : nullptr, c->sm_count, max_chunk, st));
         c->launches++;
     } else {
         const size_t smem = (size_t)V0_WARPS * V0_TABLE * sizeof(u16);
@@ -356,6 +357,7 @@ int lz4b200_set_option(lz4b200_ctx* c, const char* key, const char* value)
         if (!strcmp(value, "v0")) { c->compress_gen = 0; return 0; }
         if (!strcmp(value, "v1")) { c->compress_gen = 1; return 0; }
     }
+    if (!strcmp(key, "c1mode")) { c1_mode() = atoi(value); return 0; }
     if (!strcmp(key, "team")) {
         int t = atoi(value);
         if (t == 4 || t == 8 || t == 16 || t == 32) { c->team = t; return 0; }

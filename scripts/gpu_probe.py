@@ -30,7 +30,9 @@ for kind in kinds:
     d_bad = torch.zeros(1, dtype=torch.int32, device="cuda")
     s = torch.cuda.current_stream().cuda_stream
     for gen in gens:
-        if gen.startswith("v2t"):
+        if gen.startswith("c1m"):
+            ctx.set_option("kernels", "v2"); ctx.set_option("c1mode", gen[3:])
+        elif gen.startswith("v2t"):
             ctx.set_option("kernels", "v2"); ctx.set_option("team", gen[3:])
         else:
             ctx.set_option("kernels", gen)
@@ -50,6 +52,11 @@ for kind in kinds:
             tot = sum(pr[:8]) or 1
             print("   decode phases [ticket,load,parse,scan,literals,matches,(coop),store] %:",
                   [round(100 * x / tot, 1) for x in pr[:7]], "cycles/chunk", tot // n_chunks, flush=True)
+        if gen != "v0" and os.environ.get("PROF"):
+            ctx.set_option("prof", "1"); comp(); pr = ctx.debug_prof(); ctx.set_option("prof", "0")
+            tot = sum(pr[8:13]) or 1
+            print("   compress phases [load,match,parse,emit,final] %:", [round(100 * x / tot, 1) for x in pr[8:13]],
+                  "cycles/chunk", tot // n_chunks, "parse rounds/tile %.2f" % (pr[13] / (n_chunks * 16)), flush=True)
         total = int(d_total.item())
         ok = bool(torch.equal(d_back, d_in)) and int(d_bad.item()) == 0
         print(f"{kind} {n>>20}MiB chunk={chunk} {gen}: ratio={100*total/n:.2f}% "
