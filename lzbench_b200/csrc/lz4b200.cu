@@ -81,6 +81,10 @@ struct lz4b200_ctx {
     int compress_gen = 1;               // compress: 0 = warp per chunk, 1 = CTA per chunk (parallel match finder)
     int team = 8;                       // lanes per team for decode generation 2
     int slices = 0;                     // host entry points: number of pipeline slices (0 = automatic)
+    bool host_register = false;         // page-lock caller buffers on first sight (lzbench's are plain malloc)
+    struct Reg { const char* p; size_t n; };
+    Reg regs[16] = {};
+    int n_regs = 0;
     static constexpr int NS = 4;        // compute/H2D streams of the host pipeline
     static constexpr int MAX_SLICES = 64;
     cudaStream_t streams[NS] = {};
@@ -225,6 +229,21 @@ int decompress_slice(lz4b200_ctx* c, const u8* d_in, const u64* d_csz, const u64
     return 0;
 }
 
+// lzbench allocates inbuf/compbuf/decomp with malloc (_lzbench/lzbench.cpp:256-263) and reuses them for every
+// iteration: page-locking them once turns every later cudaMemcpyAsync into a direct DMA.  Best effort.
+void maybe_register(lz4b200_ctx* c, const char* p, size_t n)
+{
+    if (!c->host_register || n < (1u << 20)) return;
+    for (int i = 0; i < c->n_regs; i++)
+        if (p >= c->regs[i].p && p + n <= c->regs[i].p + c->regs[i].n) return;
+    if (c->n_regs == 16) return;
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, p) == cudaSuccess && attr.type != cudaMemoryTypeUnregistered) return;
+    cudaGetLastError();
+    if (cudaHostRegister(const_cast<char*>(p), n, cudaHostRegisterDefault) == cudaSuccess) c->regs[c->n_regs++] = { p, n };
+    else cudaGetLastError();
+}
+
 int check_batch(size_t n, size_t max_chunk)
 {
     if (n > 0x7FFFFFFFull) return fail(-1, "too many chunks");
@@ -329,6 +348,7 @@ void lz4b200_destroy(lz4b200_ctx* c)
     if (!c) return;
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
+    for (int i = 0; i < c->n_regs; i++) cudaHostUnregister(const_cast<char*>(c->regs[i].p));
     for (int i = 0; i < lz4b200_ctx::NS; i++) if (c->streams[i]) cudaStreamDestroy(c->streams[i]);
     if (c->d2h_stream) cudaStreamDestroy(c->d2h_stream);
     if (c->ev_sizes) cudaEventDestroy(c->ev_sizes);
@@ -362,6 +382,7 @@ int lz4b200_set_option(lz4b200_ctx* c, const char* key, const char* value)
         int t = atoi(value);
         if (t == 4 || t == 8 || t == 16 || t == 32) { c->team = t; return 0; }
     }
+    if (!strcmp(key, "host_register")) { c->host_register = value[0] == '1'; return 0; }
     if (!strcmp(key, "slices")) {
         int k = atoi(value);
         if (k >= 0 && k <= lz4b200_ctx::MAX_SLICES) { c->slices = k; return 0; }
@@ -446,6 +467,8 @@ int64_t lz4b200_compress_batch(lz4b200_ctx* c, const char* in, const size_t* chu
     u64* h_tot = h + 2 * n;
     for (size_t i = 0; i < n; i++) { h[i] = chunk_sizes[i]; total += chunk_sizes[i]; max_chunk = std::max(max_chunk, chunk_sizes[i]); }
     if (int rc = check_batch(n, max_chunk)) return rc;
+    maybe_register(c, in, total);
+    maybe_register(c, out, out_capacity);
     const size_t stride = slot_stride_for(max_chunk);
     CU(c->usz.ensure(n * 8)); CU(c->csz.ensure(n * 8));
     CU(c->d_plain.ensure(total + 16));
@@ -510,6 +533,8 @@ int64_t lz4b200_decompress_batch(lz4b200_ctx* c, const char* in, const size_t* c
         max_chunk = std::max(max_chunk, chunk_sizes[i]);
     }
     if (int rc = check_batch(n, max_chunk)) return rc;
+    maybe_register(c, in, ctotal);
+    maybe_register(c, out, total);
     CU(c->usz.ensure(n * 8)); CU(c->csz.ensure(n * 8));
     CU(c->d_plain.ensure(total + 16));
     CU(c->d_packed.ensure(ctotal + 16));

