@@ -37,7 +37,7 @@ GB = 1e9
 def parse_args():
     p = argparse.ArgumentParser()
     p.add_argument("--gpus", type=int, default=1)
-    p.add_argument("--steps", type=int, default=10)
+    p.add_argument("--steps", type=int, default=20)
     p.add_argument("--warmup", type=int, default=3)
     p.add_argument("--impl", default="b200", choices=["b200", "reference"])
     p.add_argument("--size-mib", type=int, default=1024, help="uncompressed bytes per GPU")
@@ -65,7 +65,7 @@ class ClockSampler:
         self.rows, self.proc = [], None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -77,7 +77,11 @@ class ClockSampler:
             self.rows.append((time.time(), line.strip()))
 
     def window(self, t0, t1):
-        return [r for (t, r) in self.rows if t0 - 0.05 <= t <= t1 + 0.15]
+        inside = [r for (t, r) in self.rows if t0 <= t <= t1 + 0.02]
+        if inside:
+            return inside
+        near = sorted(self.rows, key=lambda tr: min(abs(tr[0] - t0), abs(tr[0] - t1)))   # timed region shorter than
+        return [r for (_, r) in near[:3]]                                                 # the sampling period
 
     def stop(self):
         if self.proc:
@@ -243,9 +247,8 @@ def run_b200(args):
     # multi-GPU exchange step: all-gather of shard totals -> global offsets of each shard (8 B per rank)
     shard_base = 0
     if dist is not None:
-        totals = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
-        dist.all_gather(totals, d_total)
-        shard_base = int(sum(int(t.item()) for t in totals[:rank]))
+        from lzbench_b200 import sharding
+        shard_base = sharding.shard_base_offset(sharding.exchange_totals(c_total, device=dev), rank)
 
     sampler = ClockSampler(local) if rank == 0 else None
 
