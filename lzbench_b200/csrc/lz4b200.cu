@@ -10,6 +10,7 @@
 #include "kernels_v0.cuh"
 #include "kernels_v1.cuh"
 #include "kernels_v2.cuh"
+#include "kernels_v3.cuh"
 #include "kernels_c1.cuh"
 #include "staging.cuh"
 
@@ -211,7 +212,11 @@ int decompress_slice(lz4b200_ctx* c, const u8* d_in, const u64* d_csz, const u64
     scan_sizes_kernel<<<2, SCAN_THREADS, 0, st>>>(a, b, (u64)n);
     c->launches++;
     time_begin(c, st);
-    if (c->kernel_gen == 2) {
+    if (c->kernel_gen == 3) {
+        CU(v3_launch_decompress(c->team, d_in, s.coff, d_csz, s.uoff, d_usz, d_out, s.status, d_bad, (u32)n,
+                                s.ticket, c->sm_count, st));
+        c->launches += 1;
+    } else if (c->kernel_gen == 2) {
         CU(v2_launch_decompress(c->team, d_in, s.coff, d_csz, s.uoff, d_usz, d_out, s.status, d_bad, (u32)n,
                                 s.ticket, c->sm_count, st));
         c->launches += 1;
@@ -255,7 +260,7 @@ int check_batch(size_t n, size_t max_chunk)
 int plan_slices(const lz4b200_ctx* c, const size_t* chunk_sizes, size_t n, size_t total, size_t* first /* K+1 */)
 {
     int K = c->slices;
-    if (K <= 0) K = total >= (256u << 20) ? 4 : (total >= (32u << 20) ? 2 : 1);
+    if (K <= 0) K = total >= (512u << 20) ? 8 : (total >= (128u << 20) ? 4 : (total >= (32u << 20) ? 2 : 1));   // measured: scripts/e2e_probe.py
     if (K > lz4b200_ctx::MAX_SLICES) K = lz4b200_ctx::MAX_SLICES;
     if ((size_t)K > n) K = (int)n;
     size_t acc = 0, k = 1;
@@ -372,6 +377,7 @@ int lz4b200_set_option(lz4b200_ctx* c, const char* key, const char* value)
         if (!strcmp(value, "v0")) { c->kernel_gen = 0; c->compress_gen = 0; return 0; }
         if (!strcmp(value, "v1")) { c->kernel_gen = 1; c->compress_gen = 1; return 0; }
         if (!strcmp(value, "v2")) { c->kernel_gen = 2; c->compress_gen = 1; return 0; }
+        if (!strcmp(value, "v3")) { c->kernel_gen = 3; c->compress_gen = 1; return 0; }
     }
     if (!strcmp(key, "compress")) {
         if (!strcmp(value, "v0")) { c->compress_gen = 0; return 0; }
