@@ -51,8 +51,9 @@ struct C1Smem {
     static constexpr u32 OFF_RSTART = OFF_NREC + 4 * C1_NW;            // u16[NW * MAXREC]
     static constexpr u32 OFF_RLEN = OFF_RSTART + 2 * C1_NW * C1_MAXREC;
     static constexpr u32 OFF_ROFF = OFF_RLEN + 2 * C1_NW * C1_MAXREC;
-    static constexpr u32 OFF_CAPB = OFF_ROFF + 2 * C1_NW * C1_MAXREC;  // u32[NW / 32] windows with a capped match
-    static constexpr u32 OFF_LONGQ = (OFF_CAPB + 4 * (C1_NW / 32) + 15) & ~15u;   // uint4[TILE/64 + 2]
+    static constexpr u32 OFF_CAPOFF = OFF_ROFF + 2 * C1_NW * C1_MAXREC; // u16[NW] offset of a window's capped match (0 none, 0xFFFF resolved)
+    static constexpr u32 OFF_HEADQ = OFF_CAPOFF + 2 * C1_NW;           // u16[NW] windows whose long match gets finished this round
+    static constexpr u32 OFF_LONGQ = (OFF_HEADQ + 2 * C1_NW + 15) & ~15u;   // uint4[TILE/64 + 2]
     static constexpr u32 NLONG = C1_TILE / C1_LONG_LIT + 2;
     static constexpr u32 OFF_WARP = OFF_LONGQ + 16 * NLONG;            // u32[64] cross-warp scan scratch
     static constexpr u32 OFF_MISC = OFF_WARP + 4 * 64;                 // mbarrier (8 B) + scalars
@@ -139,16 +140,17 @@ compress_c1_kernel(const u8* __restrict__ in, const u64* __restrict__ in_off, co
     u16* const r_start = reinterpret_cast<u16*>(smem + C1Smem::OFF_RSTART);
     u16* const r_len = reinterpret_cast<u16*>(smem + C1Smem::OFF_RLEN);
     u16* const r_off = reinterpret_cast<u16*>(smem + C1Smem::OFF_ROFF);
-    u32* const s_capb = reinterpret_cast<u32*>(smem + C1Smem::OFF_CAPB);
+    u16* const s_capoff = reinterpret_cast<u16*>(smem + C1Smem::OFF_CAPOFF);
+    u16* const s_headq = reinterpret_cast<u16*>(smem + C1Smem::OFF_HEADQ);
     uint4* const s_longq = reinterpret_cast<uint4*>(smem + C1Smem::OFF_LONGQ);
     u32* const s_warp = reinterpret_cast<u32*>(smem + C1Smem::OFF_WARP);
     u64* const s_bar = reinterpret_cast<u64*>(smem + C1Smem::OFF_MISC);
-    u32* const s_misc = reinterpret_cast<u32*>(smem + C1Smem::OFF_MISC + 16);   // [0] chunk [1] long count [2] ext result
+    u32* const s_misc = reinterpret_cast<u32*>(smem + C1Smem::OFF_MISC + 16);   // [0] chunk [1] long-literal count [3] head count
 
     const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr u32 NWARP = C1_THREADS / 32;
     u32 phase = 0;
-    if (tid == 0) mbar_init(s_bar, 1);
+    if (tid == 0) { mbar_init(s_bar, 1); s_misc[3] = 0; }
     __syncthreads();
     long long t_prev = prof ? clock64() : 0;
     u64 t_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -257,50 +259,43 @@ compress_c1_kernel(const u8* __restrict__ in, const u64* __restrict__ in_off, co
                         s_exit[tid] = exitv;
                         s_nrec[tid] = nrec;
                     }
-                    const unsigned capw = __ballot_sync(FULL, capped);
-                    if (lane == 0) s_capb[warp] = capw;
-                    __syncthreads();
-                    // long matches: warp 0 finishes them in window order, skipping windows an earlier one covers
-                    if (warp == 0) {
-                        u32 covered = 0;
-                        for (u32 g = 0; g < NWARP; g++) {
-                            unsigned bits = s_capb[g];
-                            while (bits) {
-                                const u32 w = g * 32 + (__ffs(bits) - 1);
-                                bits &= bits - 1;
-                                const u32 k = w * C1_MAXREC;
-                                const u32 last = s_nrec[w] - 1;               // the capped match is the walk's last record
-                                const u32 p = r_start[k + last], off = r_off[k + last];
-                                u32 len = r_len[k + last];
-                                if (p < covered) continue;                     // stays uncertain; re-walked if it survives
-                                for (;;) {                                     // 128 bytes per step
-                                    const u32 a = p + len + lane * 4;
-                                    u32 c = 0;
-                                    if (a + 4 <= mlimit) {
-                                        const u32 x = c1_rd32(s_in + a) ^ c1_rd32(s_in + a - off);
-                                        c = x ? ((__ffs(x) - 1) >> 3) : 4;
-                                    } else {
-                                        while (a + c < mlimit && s_in[a + c] == s_in[a + c - off]) c++;
-                                    }
-                                    const unsigned full = __ballot_sync(FULL, c == 4);
-                                    if (full == FULL) { len += 128; continue; }
-                                    const int fl = __ffs(~full) - 1;            // first lane that stopped
-                                    len += fl * 4 + __shfl_sync(FULL, c, fl);
-                                    break;
+                    // long matches.  A run makes EVERY window inside it report a capped match; only the first window of
+                    // a stretch of capped windows (the head) is worth finishing, the others are skipped by the head's
+                    // cover one round later -- or become heads themselves if they survive.
+                    const u32 my_off = capped ? (u32)r_off[tid * C1_MAXREC + nrec - 1] : 0u;
+                    s_capoff[tid] = (u16)my_off;
+                    bool uncertain = false;
+                    if (__syncthreads_or(capped)) {
+                        if (capped && (tid == 0 || s_capoff[tid - 1] == 0)) s_headq[atomicAdd(&s_misc[3], 1u)] = (u16)tid;
+                        __syncthreads();
+                        const u32 nheads = s_misc[3];
+                        for (u32 e = warp; e < nheads; e += NWARP) {           // one warp per head, 128 bytes per step
+                            const u32 w = s_headq[e];
+                            const u32 k = w * C1_MAXREC + s_nrec[w] - 1;         // the capped match is the walk's last record
+                            const u32 p = r_start[k], off = r_off[k];
+                            u32 len = r_len[k];
+                            for (;;) {
+                                const u32 a = p + len + lane * 4;
+                                u32 c = 0;
+                                if (a + 4 <= mlimit) {
+                                    const u32 x = c1_rd32(s_in + a) ^ c1_rd32(s_in + a - off);
+                                    c = x ? ((__ffs(x) - 1) >> 3) : 4;
+                                } else {
+                                    while (a + c < mlimit && s_in[a + c] == s_in[a + c - off]) c++;
                                 }
-                                if (lane == 0) {
-                                    r_len[k + last] = (u16)len;
-                                    s_exit[w] = p + len;
-                                    s_capb[g] &= ~(1u << (w & 31));             // resolved
-                                }
-                                covered = p + len;
+                                const unsigned full = __ballot_sync(FULL, c == 4);
+                                if (full == FULL) { len += 128; continue; }
+                                const int fl = __ffs(~full) - 1;                // first lane that stopped
+                                len += fl * 4 + __shfl_sync(FULL, c, fl);
+                                break;
                             }
+                            if (lane == 0) { r_len[k] = (u16)len; s_exit[w] = p + len; s_capoff[w] = 0xFFFFu; }   // resolved
                         }
+                        __syncthreads();
+                        if (tid == 0) s_misc[3] = 0;
+                        if (capped) { if (s_capoff[tid] == 0xFFFFu) capped = false; else uncertain = true; }
+                        exitv = s_exit[tid];
                     }
-                    __syncthreads();
-                    exitv = s_exit[tid];
-                    const bool uncertain = capped && ((s_capb[warp] >> lane) & 1u);
-                    if (capped && !uncertain) capped = false;
                     // producers claim the window their chain state lands in; prefix-max picks the furthest
                     u32 key = 0;
                     if (nrec) {
