@@ -320,13 +320,19 @@ def run_b200(args):
     peak, peak_src = load_peaks()
     U, Cb = float(n), float(c_total)
 
-    def roof(kt):
+    # dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full captures under profiles/
+    # (profiles/README.md), valid for the default workload only (1 GiB mixed, 64 KiB chunks, default kernels)
+    default_cfg = args.size_mib == 1024 and chunk == 65536 and args.corpus == "mixed" and not args.kernels
+    traffic = {"decompress": 3.4846e9 if default_cfg else None,          # r01_final_decompress_v2_ncu_raw.csv
+               "compress": 2 * 0.8304e9 if default_cfg else None}        # r01_compress_c1_ncu_raw.csv (512 MiB capture x 2)
+
+    def roof(kt, which):
         if not kt:
             return None
         t = float(np.mean(kt)) * 1e-3
         ach = (U + Cb) / t / GB
         return {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                "traffic": None, "kernel_ms": t * 1e3, "launches_timed": len(kt), "peak_source": peak_src,
+                "traffic": traffic[which], "kernel_ms": t * 1e3, "launches_timed": len(kt), "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": U + Cb}
 
     line = {
@@ -341,14 +347,14 @@ def run_b200(args):
                    "compressed_pct": 100.0 * Cb / U, "kernels": args.kernels or "default",
                    "l2": "inputs larger than L2: each step reads %.0f MB and writes %.0f MB vs 126 MB L2" % (Cb / 1e6, U / 1e6),
                    "shard_base_offset": shard_base},
-        "roofline": roof(d_kt),
+        "roofline": roof(d_kt, "decompress"),
         "e2e": {"value": world * U / e2e_d / GB, "unit": "GB/s", "h2d_bytes_per_step": int(Cb + 16 * n_chunks),
                 "d2h_bytes_per_step": int(U + 4), "ms_per_step": e2e_d * 1e3,
                 "api": "lz4b200_decompress_batch (pinned host buffers)"},
         "gpu_launches": int(d_launches),
         "clocks": clocks,
         "compress": {"value": world * U / (c_ms * 1e-3) / GB, "unit": "GB/s", "ms_per_step": c_ms,
-                     "roofline": roof(c_kt), "gpu_launches": int(c_launches), "clocks": clocks_c if clocks else None,
+                     "roofline": roof(c_kt, "compress"), "gpu_launches": int(c_launches), "clocks": clocks_c if clocks else None,
                      "e2e": {"value": world * U / e2e_c / GB, "unit": "GB/s", "h2d_bytes_per_step": int(U + 8 * n_chunks),
                              "d2h_bytes_per_step": int(Cb + 8 * n_chunks + 8), "ms_per_step": e2e_c * 1e3,
                              "api": "lz4b200_compress_batch (pinned host buffers)"}},
