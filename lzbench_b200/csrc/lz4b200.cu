@@ -206,7 +206,7 @@ int compress_slice(lz4b200_ctx* c, const u8* d_in, const u64* d_usz, size_t n, s
 }
 
 int decompress_slice(lz4b200_ctx* c, const u8* d_in, const u64* d_csz, const u64* d_usz, size_t n, size_t max_chunk,
-                     u8* d_out, u32* d_bad, const Scratch& s, cudaStream_t st)
+                     u8* d_out, u32* d_bad, const Scratch& s, cudaStream_t st, int team = 0)
 {
     ScanJob a{ d_csz, s.coff, nullptr, nullptr }, b{ d_usz, s.uoff, nullptr, nullptr };
     scan_sizes_kernel<<<2, SCAN_THREADS, 0, st>>>(a, b, (u64)n);
@@ -217,7 +217,7 @@ int decompress_slice(lz4b200_ctx* c, const u8* d_in, const u64* d_csz, const u64
                                 s.ticket, c->sm_count, st));
         c->launches += 1;
     } else if (c->kernel_gen == 2) {
-        CU(v2_launch_decompress(c->team, d_in, s.coff, d_csz, s.uoff, d_usz, d_out, s.status, d_bad, (u32)n,
+        CU(v2_launch_decompress(team ? team : c->team, d_in, s.coff, d_csz, s.uoff, d_usz, d_out, s.status, d_bad, (u32)n,
                                 s.ticket, c->sm_count, st));
         c->launches += 1;
     } else if (c->kernel_gen == 1 && v1_decompress_supported(max_chunk)) {
@@ -257,10 +257,18 @@ int check_batch(size_t n, size_t max_chunk)
 }
 
 // Cut chunks [0,n) into K contiguous slices of roughly equal uncompressed size; first[k] = first chunk of slice k.
-int plan_slices(const lz4b200_ctx* c, const size_t* chunk_sizes, size_t n, size_t total, size_t* first /* K+1 */)
+// Equal slices by bytes.  Slice counts measured with scripts/e2e_probe.py (1 GiB, pinned buffers): decompress is
+// best with 16 slices (the PCIe copy of the output is the bottleneck as soon as the first slice is decoded, and
+// small slices run on wider teams with a shorter per-chunk latency), compress with 8; a geometric ramp at the
+// small end was tried and was no better.
+int plan_slices(const lz4b200_ctx* c, const size_t* chunk_sizes, size_t n, size_t total, bool decompress,
+                size_t* first /* K+1 */)
 {
     int K = c->slices;
-    if (K <= 0) K = total >= (512u << 20) ? 8 : (total >= (128u << 20) ? 4 : (total >= (32u << 20) ? 2 : 1));   // measured: scripts/e2e_probe.py
+    if (K <= 0) {
+        K = total >= (512u << 20) ? 8 : (total >= (128u << 20) ? 4 : (total >= (32u << 20) ? 2 : 1));
+        if (decompress && K >= 4) K *= 2;
+    }
     if (K > lz4b200_ctx::MAX_SLICES) K = lz4b200_ctx::MAX_SLICES;
     if ((size_t)K > n) K = (int)n;
     size_t acc = 0, k = 1;
@@ -481,7 +489,7 @@ int64_t lz4b200_compress_batch(lz4b200_ctx* c, const char* in, const size_t* chu
     CU(c->d_packed.ensure(total + total / 255 + 16 * n + 16));
     if (int rc = ensure_scratch(c, n, n * stride)) return rc;
     size_t first[lz4b200_ctx::MAX_SLICES + 1];
-    const int K = plan_slices(c, chunk_sizes, n, total, first);
+    const int K = plan_slices(c, chunk_sizes, n, total, false, first);
     if (int rc = ensure_events(c, K)) return rc;
 
     u64* running = (u64*)((u8*)c->scalars.p + SC_RUNNING);
@@ -546,7 +554,7 @@ int64_t lz4b200_decompress_batch(lz4b200_ctx* c, const char* in, const size_t* c
     CU(c->d_packed.ensure(ctotal + 16));
     if (int rc = ensure_scratch(c, n, 0)) return rc;
     size_t first[lz4b200_ctx::MAX_SLICES + 1];
-    const int K = plan_slices(c, chunk_sizes, n, total, first);
+    const int K = plan_slices(c, chunk_sizes, n, total, true, first);
     if (int rc = ensure_events(c, K)) return rc;
 
     u32* d_bad = (u32*)((u8*)c->scalars.p + SC_BAD);
@@ -563,7 +571,8 @@ int64_t lz4b200_decompress_batch(lz4b200_ctx* c, const char* in, const size_t* c
         CU(cudaStreamWaitEvent(st, c->ev_sizes, 0));
         CU(cudaMemcpyAsync((u8*)c->d_packed.p + coff, in + coff, cb, cudaMemcpyHostToDevice, st));
         int rc = decompress_slice(c, (const u8*)c->d_packed.p + coff, (const u64*)c->csz.p + f, (const u64*)c->usz.p + f,
-                                  m, max_chunk, (u8*)c->d_plain.p + uoff, d_bad, scratch_at(c, f, 0, k), st);
+                                  m, max_chunk, (u8*)c->d_plain.p + uoff, d_bad, scratch_at(c, f, 0, k), st,
+                                  m * 4 <= (size_t)c->sm_count * 32 ? 32 : (m * 2 <= (size_t)c->sm_count * 32 ? 16 : 0));
         if (rc) { cudaDeviceSynchronize(); return rc; }
         CU(cudaEventRecord(c->ev_done[k], st));
         CU(cudaStreamWaitEvent(c->d2h_stream, c->ev_done[k], 0));

@@ -13,7 +13,7 @@ h_packed = torch.empty(total, dtype=torch.uint8).pin_memory(); h_packed.copy_(h_
 h_back = torch.empty(n, dtype=torch.uint8).pin_memory()
 for gen in sys.argv[1].split(","):
     ctx.set_option("kernels", gen)
-    for K in [1, 2, 4, 8, 16, 32]:
+    for K in [0, 8, 12, 16, 24]:
         ctx.set_option("slices", str(K))
         for _ in range(2): ctx.decompress_batch(h_packed, compr, cs, h_back)
         t0 = time.perf_counter()
