@@ -11,6 +11,7 @@
 #include "kernels_v1.cuh"
 #include "kernels_v2.cuh"
 #include "kernels_v3.cuh"
+#include "kernels_v4.cuh"
 #include "kernels_c1.cuh"
 #include "staging.cuh"
 
@@ -212,7 +213,11 @@ int decompress_slice(lz4b200_ctx* c, const u8* d_in, const u64* d_csz, const u64
     scan_sizes_kernel<<<2, SCAN_THREADS, 0, st>>>(a, b, (u64)n);
     c->launches++;
     time_begin(c, st);
-    if (c->kernel_gen == 3) {
+    if (c->kernel_gen == 4) {
+        CU(v4_launch_decompress(team ? team : c->team, d_in, s.coff, d_csz, s.uoff, d_usz, d_out, s.status, d_bad, (u32)n,
+                                s.ticket, c->sm_count, st));
+        c->launches += 1;
+    } else if (c->kernel_gen == 3) {
         CU(v3_launch_decompress(c->team, d_in, s.coff, d_csz, s.uoff, d_usz, d_out, s.status, d_bad, (u32)n,
                                 s.ticket, c->sm_count, st));
         c->launches += 1;
@@ -386,6 +391,7 @@ int lz4b200_set_option(lz4b200_ctx* c, const char* key, const char* value)
         if (!strcmp(value, "v1")) { c->kernel_gen = 1; c->compress_gen = 1; return 0; }
         if (!strcmp(value, "v2")) { c->kernel_gen = 2; c->compress_gen = 1; return 0; }
         if (!strcmp(value, "v3")) { c->kernel_gen = 3; c->compress_gen = 1; return 0; }
+        if (!strcmp(value, "v4")) { c->kernel_gen = 4; c->compress_gen = 1; return 0; }
     }
     if (!strcmp(key, "compress")) {
         if (!strcmp(value, "v0")) { c->compress_gen = 0; return 0; }

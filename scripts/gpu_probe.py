@@ -32,6 +32,8 @@ for kind in kinds:
     for gen in gens:
         if gen.startswith("c1m"):
             ctx.set_option("kernels", "v2"); ctx.set_option("c1mode", gen[3:])
+        elif gen.startswith("v4t"):
+            ctx.set_option("kernels", "v4"); ctx.set_option("team", gen[3:])
         elif gen.startswith("v3t"):
             ctx.set_option("kernels", "v3"); ctx.set_option("team", gen[3:])
         elif gen.startswith("v2t"):
