@@ -19,7 +19,7 @@
 namespace lz4b200 {
 
 template <u32 T>
-__global__ void __launch_bounds__(V2_BLOCK)
+__global__ void __launch_bounds__(V2_BLOCK, 7)     // <= 72 registers: 28 warps = 112 teams per SM, one wave for 16384 chunks
 decompress_v4_kernel(const u8* __restrict__ in, const u64* __restrict__ in_off, const u64* __restrict__ csz,
                      const u64* __restrict__ out_off, const u64* __restrict__ usz, u8* out,
                      u32* __restrict__ status, u32* __restrict__ bad_chunks, u32 n_chunks, u32* ticket)
@@ -54,67 +54,89 @@ decompress_v4_kernel(const u8* __restrict__ in, const u64* __restrict__ in_off, 
         }                                                                                    \
     } while (0)
 
+    u32 op_safe = 0, ip_safe = 0;                      // fast path allowed while op + L <= op_safe and ip + L <= ip_safe
+    bool fastable = false;                             // busy, not a raw chunk, big enough for the fast path at all
+    u32 rem = 0, roff = 0;                             // long match in progress: bytes still owed, its offset
+
     for (;;) {
         // ---- A: decode the current token of every team (warp level, no branches) ----
-        const u32 L = tok >> 4, M = tok & ML_MASK;
-        const u32 ml = M + MINMATCH, cpy = op + L, nip = ip + 1 + L + 2;
-        u32 sel_lo = xb[0], sel_hi = xb[0];
+        // A match longer than 18 bytes (token nibble 15 + one length byte) is executed 18 bytes per iteration:
+        // `rem` bytes are still owed at offset `roff`; while rem != 0 the (already prefetched) next token waits.
+        const bool cont = rem != 0;
+        const u32 Lt = tok >> 4, M = tok & ML_MASK;
+        const u32 L = cont ? 0u : Lt;
+        const u32 cpy = op + L;
+        u32 sel_lo = xb[0], sel_hi = xb[0], sel_e = xb[0];
         #pragma unroll
-        for (u32 k = 1; k < NX; k++) { if (L / T == k) sel_lo = xb[k]; if ((L + 1) / T == k) sel_hi = xb[k]; }
-        const u32 lo = __shfl_sync(FULL, sel_lo, tbase + (L & (T - 1)));
-        const u32 hi = __shfl_sync(FULL, sel_hi, tbase + ((L + 1) & (T - 1)));
-        const u32 off = lo | (hi << 8);
-        // fast: short literal run, short non-overlapping match, valid offset, far from both ends of the block
-        const bool f = busy && L < RUN_MASK && M < ML_MASK && clen != n &&
-                       cpy + ml + MFLIMIT <= n && ip + 1 + L + (2 + 1 + LASTLITERALS) <= clen &&
-                       off >= ml && off <= cpy;
+        for (u32 k = 1; k < NX; k++) {
+            if (Lt / T == k) sel_lo = xb[k];
+            if ((Lt + 1) / T == k) sel_hi = xb[k];
+            if ((Lt + 2) / T == k) sel_e = xb[k];
+        }
+        const u32 lo = __shfl_sync(FULL, sel_lo, tbase + (Lt & (T - 1)));
+        const u32 hi = __shfl_sync(FULL, sel_hi, tbase + ((Lt + 1) & (T - 1)));
+        const u32 e = __shfl_sync(FULL, sel_e, tbase + ((Lt + 2) & (T - 1)));     // length byte, if the nibble is 15
+        const bool ext = M == ML_MASK;
+        const u32 off = cont ? roff : (lo | (hi << 8));
+        const u32 ml_total = cont ? rem : (ext ? 19u + e : M + MINMATCH);
+        const u32 ml = ml_total < 18u ? ml_total : 18u;                           // this iteration's part
+        const u32 nip = ip + Lt + 3 + (ext ? 1u : 0u);
+        // fast: short literal run, non-overlapping match of <= 273 bytes, valid offset, far enough from both ends
+        // of the block that (a) this is not the last sequence (lz4/lz4.c:1990), (b) the match ends 12 bytes
+        // before the end and (c) the next window can be read unchecked
+        const bool f = fastable && (cont || (tok < 0xF0u && (!ext || (Lt <= 13u && e != 255u)) &&
+                                            cpy + ml_total <= op_safe && ip + Lt <= ip_safe && off <= cpy)) &&
+                       off >= ml;
 
-        // ---- B: store the previous sequence's match (loaded one iteration ago), every lane its own positions ----
+        // ---- B: store the previous part's match bytes (loaded one iteration ago), every lane its own positions ----
         {
             const u32 i0 = (j - pm_dst) & (T - 1);
             const u32 sl = tbase + ((j - pm_off) & (T - 1));
+            u8* p = dst + (pm_dst + i0);
             #pragma unroll
             for (u32 k = 0; k < NM; k++) {
                 const u32 val = __shfl_sync(FULL, pvb[k], sl);
-                const u32 i = i0 + k * T;
-                if (i < pm_len) dst[pm_dst + i] = (u8)val;
+                if (i0 + k * T < pm_len) p[k * T] = (u8)val;
             }
             pm_len = 0;
         }
         // ---- C: literal run, window order -> position order ----
         {
             const u32 i0 = (j - op) & (T - 1);
+            u8* p = dst + (op + i0);
+            const u32 lim = f ? L : 0u;
             #pragma unroll
             for (u32 k = 0; k < NX; k++) {
                 const u32 val = __shfl_sync(FULL, xb[k], tbase + i0);
-                const u32 i = i0 + k * T;
-                if (f && i < L) dst[op + i] = (u8)val;
+                if (i0 + k * T < lim) p[k * T] = (u8)val;
             }
         }
-        // ---- D: next token + window, and this match's source (stored next iteration) ----
+        // ---- D: this part's source (stored next iteration); at the first part also the next token + window ----
         if (f) {
-            if (j == 0 && ((nip + V3_AHEAD) ^ (ip + V3_AHEAD)) >= 128u && nip + V3_AHEAD < clen)
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(src + ((nip + V3_AHEAD) & ~127u)));
             const u32 sbase = cpy - off;
             const u32 t0 = (j - sbase) & (T - 1);
+            const u8* q = dst + (sbase + t0);
             #pragma unroll
-            for (u32 k = 0; k < NM; k++) { const u32 t = t0 + k * T; pvb[k] = t < ml ? (u32)dst[sbase + t] : 0u; }
+            for (u32 k = 0; k < NM; k++) pvb[k] = t0 + k * T < ml ? (u32)q[k * T] : 0u;
             pm_len = ml; pm_dst = cpy; pm_off = off;
-            tok = __ldg(src + nip);                     // nip <= clen - 6
-            #pragma unroll
-            for (u32 k = 0; k < NX; k++) {
-                const u32 i = nip + 1 + j + k * T;
-                xb[k] = i < clen ? (u32)__ldg(src + i) : 0u;
+            if (!cont) {
+                const u8* s_ = src + nip;               // nip + 17 <= clen: unchecked reads
+                tok = __ldg(s_);
+                #pragma unroll
+                for (u32 k = 0; k < NX; k++) xb[k] = (u32)__ldg(s_ + 1 + j + k * T);
+                ip = nip; roff = off;
             }
-            ip = nip; op = cpy + ml;
+            rem = ml_total - ml;
+            op = cpy + ml;
         }
 
+        // ---- E + F: everything else, behind one vote ----
+        if (!__any_sync(FULL, (busy && !f) || !busy)) continue;
         u32 wl_len = 0, wl_ip = 0, wl_op = 0;          // warp-wide literal copy request
         u32 wm_len = 0, wm_op = 0, wm_off = 0;         // warp-wide match copy request
         u32 err = ST_OK;
         bool finished = false;
-
-        // ---- E: slow block -- one sequence through the general path for the teams that need it ----
+        // E: slow block -- one sequence through the general path for the teams that need it
         if (__any_sync(FULL, busy && !f)) {
             __syncwarp();                               // mapped stores above -> visible to the unmapped copies below
             if (busy && !f) {
@@ -186,7 +208,7 @@ decompress_v4_kernel(const u8* __restrict__ in, const u64* __restrict__ in_off, 
         }
 
         // ---- management, behind one vote: long copies by the whole warp, chunk completion, next chunk ----
-        if (__any_sync(FULL, !busy || finished || (wl_len | wm_len) != 0)) {
+        {
             unsigned todo = __ballot_sync(FULL, j == 0 && (wl_len | wm_len) != 0);
             while (todo) {
                 const int l = __ffs(todo) - 1; todo &= todo - 1;
@@ -211,7 +233,7 @@ decompress_v4_kernel(const u8* __restrict__ in, const u64* __restrict__ in_off, 
                     status[chunk] = err;
                     if (err && bad_chunks) atomicAdd(bad_chunks, 1u);
                 }
-                busy = false;
+                busy = false; fastable = false;
             }
             if (!busy && !exhausted) {
                 u32 c = 0;
@@ -223,8 +245,10 @@ decompress_v4_kernel(const u8* __restrict__ in, const u64* __restrict__ in_off, 
                     src = in + in_off[c]; clen = (u32)csz[c];
                     dst = out + out_off[c]; n = (u32)usz[c];
                     ip = 0; op = 0; busy = true; pm_len = 0;
-                    if (j * 128u < clen && j * 128u < V3_AHEAD + 128u)         // first lines of the compressed chunk
-                        asm volatile("prefetch.global.L2 [%0];" ::"l"(src + j * 128u));
+                    fastable = clen != n && n >= 32 && clen >= 24;
+                    op_safe = fastable ? n - MFLIMIT : 0;          // match end + MFLIMIT <= n (non-last sequence, lz4/lz4.c:1990,:2139)
+                    ip_safe = fastable ? clen - 21 : 0;            // next window (17 bytes at ip + L + 3 or 4) stays inside the chunk
+                    rem = 0;
                     V3_PREFETCH(0);
                 }
             }
