@@ -105,7 +105,9 @@ int lz4b200_debug_prof(lz4b200_ctx* ctx, uint64_t* out16);
 
 /* Tunable: which decode kernel generation to run: "kernels" = "v0" (warp per chunk), "v1"
  * (one CTA per chunk, TMA-staged shared-memory tile, speculative parallel parse), "v2"
- * (sub-warp teams, default); "team" = "4"/"8"/"16"/"32" lanes per chunk for v2.  "compress" = "v0"/"v1" picks the compressor generation; "slices" = number of H2D/kernel/D2H
+ * (sub-warp teams), "v3" (v2 + every output byte owned by a fixed lane, match store pipelined one sequence behind
+ * its load, no barriers on the fast path), "v4" (v3 with a warp-uniform, predicated fast path; default);
+ * "team" = "8"/"16" lanes per chunk (v2 also "4"/"32").  "compress" = "v0"/"v1" picks the compressor generation; "slices" = number of H2D/kernel/D2H
  * pipeline slices of the host entry points (0 = automatic); "host_register" = "1" page-locks caller
  * buffers on first sight (what the lzbench wrappers turn on).  Also "timing" = "0"/"1" (see above).  Returns 0, or -1 for an unknown key or value.
  * Default kernels: the fastest verified generation. */

@@ -79,7 +79,7 @@ struct PinBuf {
 struct lz4b200_ctx {
     int device = 0;
     int sm_count = 148;
-    int kernel_gen = 2;                 // decode: 0 = warp per chunk, 1 = CTA tile (TMA), 2 = sub-warp teams
+    int kernel_gen = 4;                 // decode: 0 warp per chunk, 1 CTA tile (TMA), 2 sub-warp teams, 3 + mapped lanes / pipelined match, 4 + warp-uniform fast path (default)
     int compress_gen = 1;               // compress: 0 = warp per chunk, 1 = CTA per chunk (parallel match finder)
     int team = 8;                       // lanes per team for decode generation 2
     int slices = 0;                     // host entry points: number of pipeline slices (0 = automatic)
@@ -339,6 +339,8 @@ int lz4b200_create(int device, size_t max_total_bytes, size_t max_chunk_bytes, l
     const char* gen = getenv("LZ4B200_KERNELS");
     if (gen && !strcmp(gen, "v0")) { c->kernel_gen = 0; c->compress_gen = 0; }
     if (gen && !strcmp(gen, "v1")) c->kernel_gen = 1;
+    if (gen && !strcmp(gen, "v2")) c->kernel_gen = 2;
+    if (gen && !strcmp(gen, "v3")) c->kernel_gen = 3;
     for (int i = 0; i < lz4b200_ctx::NS; i++) {
         cudaError_t e = cudaStreamCreateWithFlags(&c->streams[i], cudaStreamNonBlocking);
         if (e != cudaSuccess) { lz4b200_destroy(c); return fail(-2, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
