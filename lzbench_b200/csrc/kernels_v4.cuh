@@ -93,6 +93,7 @@ decompress_v4_kernel(const u8* __restrict__ in, const u64* __restrict__ in_off, 
             const u32 i0 = (j - pm_dst) & (T - 1);
             const u32 sl = tbase + ((j - pm_off) & (T - 1));
             u8* p = dst + (pm_dst + i0);
+            asm volatile("" : "+l"(p));              // one address computation for the predicated stores below
             #pragma unroll
             for (u32 k = 0; k < NM; k++) {
                 const u32 val = __shfl_sync(FULL, pvb[k], sl);
@@ -104,6 +105,7 @@ decompress_v4_kernel(const u8* __restrict__ in, const u64* __restrict__ in_off, 
         {
             const u32 i0 = (j - op) & (T - 1);
             u8* p = dst + (op + i0);
+            asm volatile("" : "+l"(p));
             const u32 lim = f ? L : 0u;
             #pragma unroll
             for (u32 k = 0; k < NX; k++) {
@@ -116,6 +118,7 @@ decompress_v4_kernel(const u8* __restrict__ in, const u64* __restrict__ in_off, 
             const u32 sbase = cpy - off;
             const u32 t0 = (j - sbase) & (T - 1);
             const u8* q = dst + (sbase + t0);
+            asm volatile("" : "+l"(q));
             #pragma unroll
             for (u32 k = 0; k < NM; k++) pvb[k] = t0 + k * T < ml ? (u32)q[k * T] : 0u;
             pm_len = ml; pm_dst = cpy; pm_off = off;
