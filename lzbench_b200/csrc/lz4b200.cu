@@ -13,6 +13,7 @@
 #include "kernels_v3.cuh"
 #include "kernels_v4.cuh"
 #include "kernels_c1.cuh"
+#include "kernels_c2.cuh"
 #include "staging.cuh"
 
 #include <algorithm>
@@ -80,7 +81,7 @@ struct lz4b200_ctx {
     int device = 0;
     int sm_count = 148;
     int kernel_gen = 4;                 // decode: 0 warp per chunk, 1 CTA tile (TMA), 2 sub-warp teams, 3 + mapped lanes / pipelined match, 4 + warp-uniform fast path (default)
-    int compress_gen = 1;               // compress: 0 = warp per chunk, 1 = CTA per chunk (parallel match finder)
+    int compress_gen = 2;               // compress: 0 warp per chunk, 1 CTA per chunk (parallel match finder + speculative parse), 2 = 1 with the phases on two warp groups (default)
     int team = 8;                       // lanes per team for decode generation 2
     int slices = 0;                     // host entry points: number of pipeline slices (0 = automatic)
     bool host_register = false;         // page-lock caller buffers on first sight (lzbench's are plain malloc)
@@ -178,7 +179,10 @@ int compress_slice(lz4b200_ctx* c, const u8* d_in, const u64* d_usz, size_t n, s
     c->launches++;
 
     time_begin(c, st);
-    if (c->compress_gen == 1 && c1_compress_supported(max_chunk)) {
+    if (c->compress_gen == 2 && c1_compress_supported(max_chunk)) {
+        CU(c2_launch_compress(d_in, s.uoff, d_usz, s.stage, stride, d_csz, (u32)n, s.ticket, c->sm_count, st));
+        c->launches++;
+    } else if (c->compress_gen == 1 && c1_compress_supported(max_chunk)) {
         CU(c1_launch_compress(d_in, s.uoff, d_usz, s.stage, stride, d_csz, (u32)n, s.ticket,
                               c->prof_on ? (u64*)c->prof.p : nullptr, c->sm_count, max_chunk, st));
         c->launches++;
@@ -390,14 +394,15 @@ int lz4b200_set_option(lz4b200_ctx* c, const char* key, const char* value)
     if (!c || !key || !value) return -1;
     if (!strcmp(key, "kernels")) {          // decode generation (and v0 also selects the v0 compressor)
         if (!strcmp(value, "v0")) { c->kernel_gen = 0; c->compress_gen = 0; return 0; }
-        if (!strcmp(value, "v1")) { c->kernel_gen = 1; c->compress_gen = 1; return 0; }
-        if (!strcmp(value, "v2")) { c->kernel_gen = 2; c->compress_gen = 1; return 0; }
-        if (!strcmp(value, "v3")) { c->kernel_gen = 3; c->compress_gen = 1; return 0; }
-        if (!strcmp(value, "v4")) { c->kernel_gen = 4; c->compress_gen = 1; return 0; }
+        if (!strcmp(value, "v1")) { c->kernel_gen = 1; c->compress_gen = 1; return 0; }      // first tiled generation of both
+        if (!strcmp(value, "v2")) { c->kernel_gen = 2; c->compress_gen = 2; return 0; }
+        if (!strcmp(value, "v3")) { c->kernel_gen = 3; c->compress_gen = 2; return 0; }
+        if (!strcmp(value, "v4")) { c->kernel_gen = 4; c->compress_gen = 2; return 0; }
     }
     if (!strcmp(key, "compress")) {
         if (!strcmp(value, "v0")) { c->compress_gen = 0; return 0; }
         if (!strcmp(value, "v1")) { c->compress_gen = 1; return 0; }
+        if (!strcmp(value, "v2")) { c->compress_gen = 2; return 0; }
     }
     if (!strcmp(key, "c1mode")) { c1_mode() = atoi(value); return 0; }
     if (!strcmp(key, "team")) {

@@ -30,7 +30,9 @@ for kind in kinds:
     d_bad = torch.zeros(1, dtype=torch.int32, device="cuda")
     s = torch.cuda.current_stream().cuda_stream
     for gen in gens:
-        if gen.startswith("c1m"):
+        if gen in ("c1", "c2"):
+            ctx.set_option("kernels", "v4"); ctx.set_option("compress", "v" + gen[1])
+        elif gen.startswith("c1m"):
             ctx.set_option("kernels", "v2"); ctx.set_option("c1mode", gen[3:])
         elif gen.startswith("v4t"):
             ctx.set_option("kernels", "v4"); ctx.set_option("team", gen[3:])
