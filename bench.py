@@ -143,6 +143,35 @@ def cpu_baseline(plain: np.ndarray, chunk: int, sample_bytes: int, threads: int,
             "compr_sizes": compr}
 
 
+def lzbench_row(sample: np.ndarray, chunk: int):
+    """The stock `lz4 1.9.3` row of the reference's OWN harness (oracle/_ref/lzbench_ref = unmodified lzbench.cpp
+    compiled from the reference tree): `lzbench -elz4 -b<chunk KiB>` on the same sample, single thread."""
+    import re
+    import tempfile
+    exe = os.path.join(ROOT, "oracle", "_ref", "lzbench_ref")
+    if not os.path.exists(exe) or chunk % 1024:
+        return None
+    d = "/dev/shm" if os.path.isdir("/dev/shm") else None
+    try:
+        with tempfile.NamedTemporaryFile(suffix=".bin", dir=d, delete=False) as f:
+            sample.tofile(f)
+            path = f.name
+        r = subprocess.run([exe, "-elz4", f"-b{chunk // 1024}", "-t1,1", "-x", path], capture_output=True, text=True, timeout=120)
+        for line in (r.stdout + r.stderr).splitlines():
+            m = re.match(r"^lz4 1\.9\.3\s+(\d+) MB/s\s+(\d+) MB/s\s+(\d+)\s+([\d.]+)", line)
+            if m:
+                return {"command": f"lzbench -elz4 -b{chunk // 1024} -t1,1 -x <sample>", "compress_MBps": int(m.group(1)),
+                        "decompress_MBps": int(m.group(2)), "compressed_bytes": int(m.group(3)), "ratio_pct": float(m.group(4))}
+    except Exception:
+        return None
+    finally:
+        try:
+            os.unlink(path)
+        except Exception:
+            pass
+    return None
+
+
 def _ref_trampolines():
     """C-level lzbench plugin wrappers around oracle/_ref, compiled once into oracle/_ref (git-ignored)."""
     so = os.path.join(ROOT, "oracle", "_ref", "libref_plugin.so")
@@ -373,6 +402,7 @@ def run_b200(args):
             "compress_GBps": cb["threads"][threads]["compress_GBps"],
             "compress_single_thread_GBps": cb["threads"][1]["compress_GBps"],
             "ratio_pct": 100.0 * cb["compressed_bytes"] / cb["sample_bytes"]}
+        line["cpu_baseline"]["lzbench_row"] = lzbench_row(h_plain.numpy()[:min(sample, 256 << 20)], chunk)
         line["compress"]["ratio_pct"] = 100.0 * Cb / U
         line["compress"]["size_vs_reference"] = gpu_sample_bytes / cb["compressed_bytes"]
     print(json.dumps(line), flush=True)
