@@ -82,7 +82,7 @@ struct lz4b200_ctx {
     int sm_count = 148;
     int kernel_gen = 4;                 // decode: 0 warp per chunk, 1 CTA tile (TMA), 2 sub-warp teams, 3 + mapped lanes / pipelined match, 4 + warp-uniform fast path (default)
     int compress_gen = 2;               // compress: 0 warp per chunk, 1 CTA per chunk (parallel match finder + speculative parse), 2 = 1 with the phases on two warp groups (default)
-    int team = 8;                       // lanes per team for decode generation 2
+    int team = 0;                       // lanes per chunk for the team decoders: 8 / 16 / 32, 0 = by batch size
     int slices = 0;                     // host entry points: number of pipeline slices (0 = automatic)
     bool host_register = false;         // page-lock caller buffers on first sight (lzbench's are plain malloc)
     struct Reg { const char* p; size_t n; };
@@ -217,16 +217,24 @@ int decompress_slice(lz4b200_ctx* c, const u8* d_in, const u64* d_csz, const u64
     scan_sizes_kernel<<<2, SCAN_THREADS, 0, st>>>(a, b, (u64)n);
     c->launches++;
     time_begin(c, st);
-    if (c->kernel_gen == 4) {
-        CU(v4_launch_decompress(team ? team : c->team, d_in, s.coff, d_csz, s.uoff, d_usz, d_out, s.status, d_bad, (u32)n,
+    // team width: with few chunks per launch the run time is the latency of one chunk's chain, which is shorter
+    // on wider teams, and wider teams also spread few chunks over more SMs
+    if (!team) team = c->team;
+    if (!team) team = n * 4 <= (size_t)c->sm_count * 32 ? 32 : (n * 2 <= (size_t)c->sm_count * 32 ? 16 : 8);
+    if (c->kernel_gen == 4 && team != 32) {
+        CU(v4_launch_decompress(team, d_in, s.coff, d_csz, s.uoff, d_usz, d_out, s.status, d_bad, (u32)n,
+                                s.ticket, c->sm_count, st));
+        c->launches += 1;
+    } else if (c->kernel_gen == 4) {                    // one warp per chunk: the v2 kernel at T = 32
+        CU(v2_launch_decompress(32, d_in, s.coff, d_csz, s.uoff, d_usz, d_out, s.status, d_bad, (u32)n,
                                 s.ticket, c->sm_count, st));
         c->launches += 1;
     } else if (c->kernel_gen == 3) {
-        CU(v3_launch_decompress(c->team, d_in, s.coff, d_csz, s.uoff, d_usz, d_out, s.status, d_bad, (u32)n,
+        CU(v3_launch_decompress(team == 32 ? 16 : team, d_in, s.coff, d_csz, s.uoff, d_usz, d_out, s.status, d_bad, (u32)n,
                                 s.ticket, c->sm_count, st));
         c->launches += 1;
     } else if (c->kernel_gen == 2) {
-        CU(v2_launch_decompress(team ? team : c->team, d_in, s.coff, d_csz, s.uoff, d_usz, d_out, s.status, d_bad, (u32)n,
+        CU(v2_launch_decompress(team, d_in, s.coff, d_csz, s.uoff, d_usz, d_out, s.status, d_bad, (u32)n,
                                 s.ticket, c->sm_count, st));
         c->launches += 1;
     } else if (c->kernel_gen == 1 && v1_decompress_supported(max_chunk)) {
@@ -407,7 +415,7 @@ int lz4b200_set_option(lz4b200_ctx* c, const char* key, const char* value)
     if (!strcmp(key, "c1mode")) { c1_mode() = atoi(value); return 0; }
     if (!strcmp(key, "team")) {
         int t = atoi(value);
-        if (t == 4 || t == 8 || t == 16 || t == 32) { c->team = t; return 0; }
+        if (t == 0 || t == 4 || t == 8 || t == 16 || t == 32) { c->team = t; return 0; }
     }
     if (!strcmp(key, "host_register")) { c->host_register = value[0] == '1'; return 0; }
     if (!strcmp(key, "slices")) {
@@ -584,8 +592,7 @@ int64_t lz4b200_decompress_batch(lz4b200_ctx* c, const char* in, const size_t* c
         CU(cudaStreamWaitEvent(st, c->ev_sizes, 0));
         CU(cudaMemcpyAsync((u8*)c->d_packed.p + coff, in + coff, cb, cudaMemcpyHostToDevice, st));
         int rc = decompress_slice(c, (const u8*)c->d_packed.p + coff, (const u64*)c->csz.p + f, (const u64*)c->usz.p + f,
-                                  m, max_chunk, (u8*)c->d_plain.p + uoff, d_bad, scratch_at(c, f, 0, k), st,
-                                  m * 4 <= (size_t)c->sm_count * 32 ? 32 : (m * 2 <= (size_t)c->sm_count * 32 ? 16 : 0));
+                                  m, max_chunk, (u8*)c->d_plain.p + uoff, d_bad, scratch_at(c, f, 0, k), st);
         if (rc) { cudaDeviceSynchronize(); return rc; }
         CU(cudaEventRecord(c->ev_done[k], st));
         CU(cudaStreamWaitEvent(c->d2h_stream, c->ev_done[k], 0));
