@@ -99,8 +99,13 @@ __device__ __forceinline__ u32 c2_block_excl(u32 v, u32* warp_scratch, u32& tota
 template <int MODE>
 __global__ void __launch_bounds__(C2_THREADS, 2)
 compress_c2_kernel(const u8* __restrict__ in, const u64* __restrict__ in_off, const u64* __restrict__ usz,
-                   u8* __restrict__ stage, u64 slot_stride, u64* __restrict__ csz, u32 n_chunks, u32* ticket)
+                   u8* __restrict__ stage, u64 slot_stride, u64* __restrict__ csz, u32 n_chunks_arg, u32* ticket,
+                   const u64* __restrict__ n_dev, u32* __restrict__ tail_pos, u32* __restrict__ tail_len,
+                   const u32* __restrict__ hist_arr)
 {
+    // segmented mode (segmented.cuh): the job count lives in device memory and every job also reports where its
+    // last_literals record starts and how many literals it holds
+    const u32 n_chunks = n_dev ? (u32)*n_dev : n_chunks_arg;
     extern __shared__ __align__(128) u8 smem[];
     u8* const s_in_raw = smem + C2Smem::OFF_IN;
     u16* const s_tab = reinterpret_cast<u16*>(smem + C2Smem::OFF_TAB);
@@ -151,14 +156,17 @@ compress_c2_kernel(const u8* __restrict__ in, const u64* __restrict__ in_off, co
             if (tid >= 32 && tid - 32 < n - tail0) s_in[tail0 + tid - 32] = src[tail0 + tid - 32];
             uint4* t4 = reinterpret_cast<uint4*>(s_tab);
             for (u32 i = tid; i < (2u << C1_HBITS) / 16; i += C2_THREADS) t4[i] = make_uint4(0, 0, 0, 0);
-            if (tid == 0) { s_misc[4] = 0; s_misc[5] = 0; }
+            if (tid == 0) { s_misc[4] = hist_arr ? (hist_arr[chunk] & 0x7FFFFFFFu) : 0u; s_misc[5] = 0; }   // chain starts after the history
             if (bulk) { mbar_wait(s_bar, phase); phase ^= 1; }
         }
         __syncthreads();
 
         if (n >= MIN_LENGTH) {
-            const u32 mfl = n - MFLIMIT;                // last position a match may start at
-            const u32 mlimit = n - LASTLITERALS;        // matches end at or before this
+            // a job that is not the end of its chunk (segmented mode, bit 31 of hist_arr) may match right up to its
+            // last byte: the end-of-block rules (lz4/lz4.c:883-884) bind only the real end of the block
+            const bool inner = hist_arr && (hist_arr[chunk] >> 31);
+            const u32 mfl = n - (inner ? MINMATCH : MFLIMIT);      // last position a match may start at
+            const u32 mlimit = n - (inner ? 0u : LASTLITERALS);    // matches end at or before this
             const u32 n_tiles = mfl / C1_TILE + 1;
             if (grp == 0) {
                 // ======== group A: match finding, one tile ahead of group B ========
@@ -208,7 +216,7 @@ compress_c2_kernel(const u8* __restrict__ in, const u64* __restrict__ in_off, co
                 }
             } else {
                 // ======== group B: parse + emit ========
-                u32 cur = 0;                                // chain state: end of the last match (= literal anchor)
+                u32 cur = hist_arr ? (hist_arr[chunk] & 0x7FFFFFFFu) : 0u;  // chain state: end of the last match (= literal anchor)
                 u32 op = 0;                                 // bytes emitted so far
                 for (u32 t = 0; t < n_tiles; t++) {
                     const u32 t0 = t * C1_TILE, buf = t & 1;
@@ -374,6 +382,7 @@ compress_c2_kernel(const u8* __restrict__ in, const u64* __restrict__ in_off, co
                 if (last >= RUN_MASK) c1_put_ext(o + 1, last - RUN_MASK);
             }
             for (u32 i = tid; i < last; i += C2_THREADS) o[hdr + i] = s_in[cur + i];
+            if (tid == 0 && tail_pos) { tail_pos[chunk] = op; tail_len[chunk] = last; }
             op += hdr + last;
             if (tid == 0) csz[chunk] = op;
         }
@@ -383,7 +392,7 @@ compress_c2_kernel(const u8* __restrict__ in, const u64* __restrict__ in_off, co
 
 template <int MODE>
 inline cudaError_t c2_launch_mode(const u8* in, const u64* in_off, const u64* usz, u8* stage, u64 stride, u64* csz,
-                                  u32 n, u32* ticket, int sm_count, cudaStream_t st)
+                                  u32 n, u32* ticket, int sm_count, cudaStream_t st, const u64* n_dev, u32* tail_pos, u32* tail_len, const u32* hist)
 {
     static bool attr = false;
     if (!attr) {
@@ -396,17 +405,18 @@ inline cudaError_t c2_launch_mode(const u8* in, const u64* in_off, const u64* us
     if (grid > n) grid = n;
     cudaError_t e = cudaMemsetAsync(ticket, 0, sizeof(u32), st);
     if (e != cudaSuccess) return e;
-    compress_c2_kernel<MODE><<<grid, C2_THREADS, C2Smem::BYTES, st>>>(in, in_off, usz, stage, stride, csz, n, ticket);
+    compress_c2_kernel<MODE><<<grid, C2_THREADS, C2Smem::BYTES, st>>>(in, in_off, usz, stage, stride, csz, n, ticket, n_dev, tail_pos, tail_len, hist);
     return cudaGetLastError();
 }
 
 inline cudaError_t c2_launch_compress(const u8* in, const u64* in_off, const u64* usz, u8* stage, u64 stride, u64* csz,
-                                      u32 n, u32* ticket, int sm_count, cudaStream_t st)
+                                      u32 n, u32* ticket, int sm_count, cudaStream_t st, const u64* n_dev = nullptr,
+                                      u32* tail_pos = nullptr, u32* tail_len = nullptr, const u32* hist = nullptr)
 {
     switch (c1_mode()) {
-    case 0:  return c2_launch_mode<0>(in, in_off, usz, stage, stride, csz, n, ticket, sm_count, st);
-    case 2:  return c2_launch_mode<2>(in, in_off, usz, stage, stride, csz, n, ticket, sm_count, st);
-    default: return c2_launch_mode<1>(in, in_off, usz, stage, stride, csz, n, ticket, sm_count, st);
+    case 0:  return c2_launch_mode<0>(in, in_off, usz, stage, stride, csz, n, ticket, sm_count, st, n_dev, tail_pos, tail_len, hist);
+    case 2:  return c2_launch_mode<2>(in, in_off, usz, stage, stride, csz, n, ticket, sm_count, st, n_dev, tail_pos, tail_len, hist);
+    default: return c2_launch_mode<1>(in, in_off, usz, stage, stride, csz, n, ticket, sm_count, st, n_dev, tail_pos, tail_len, hist);
     }
 }
 

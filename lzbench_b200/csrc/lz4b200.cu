@@ -14,6 +14,7 @@
 #include "kernels_v4.cuh"
 #include "kernels_c1.cuh"
 #include "kernels_c2.cuh"
+#include "segmented.cuh"
 #include "staging.cuh"
 
 #include <algorithm>
@@ -88,6 +89,7 @@ struct lz4b200_ctx {
     struct Reg { const char* p; size_t n; };
     Reg regs[16] = {};
     int n_regs = 0;
+    size_t seg_chunks = 0;              // chunk count the segmented job arrays are laid out for (current call)
     static constexpr int NS = 4;        // compute/H2D streams of the host pipeline
     static constexpr int MAX_SLICES = 64;
     cudaStream_t streams[NS] = {};
@@ -105,7 +107,8 @@ struct lz4b200_ctx {
     DevBuf status;                      // u32[n_chunks]
     DevBuf prof;                        // u64[16] phase-cycle counters (debug option "prof")
     bool prof_on = false;
-    DevBuf stage;                       // compress: n_chunks slots of slot_stride bytes
+    DevBuf stage;                       // compress: n_chunks slots of slot_stride bytes (or one slot per 64 KiB segment)
+    DevBuf seg64, seg32;                // segmented compress (segmented.cuh): u64 / u32 job arrays
     // buffers behind the host entry points
     DevBuf d_plain, d_packed;
     PinBuf h_sizes;                     // u64[2*n_chunks + MAX_SLICES + 2]
@@ -117,12 +120,14 @@ namespace {
 constexpr size_t SC_TOTAL = 0;          // u64  total compressed size (device entry point without caller buffer)
 constexpr size_t SC_BAD = 8;            // u32  malformed-chunk counter
 constexpr size_t SC_TICKETS = 256;      // u32[MAX_SLICES] work tickets, one per slice
+constexpr size_t SC_NJOBS = 1024;        // u64[MAX_SLICES] job counts of the segmented compressor, one per slice
 constexpr size_t SC_RUNNING = 4096;     // u64[MAX_SLICES] running compressed totals after each slice
 constexpr size_t SC_BYTES = 8192;
 
 // per-slice view of the scratch arrays: slices of one host call run concurrently on different streams
 struct Scratch {
     u64* uoff; u64* coff; u32* status; u8* stage; u32* ticket;
+    size_t first_chunk;                // slices of one call own disjoint regions of the per-chunk / per-job arrays
 };
 
 void time_begin(lz4b200_ctx* c, cudaStream_t st)
@@ -145,6 +150,24 @@ size_t slot_stride_for(size_t max_chunk)
     return (b + 15) & ~size_t(15);
 }
 
+bool segmented(const lz4b200_ctx* c, size_t max_chunk) { return c->compress_gen >= 1 && max_chunk > SEG_BYTES; }
+size_t segs_per_chunk(size_t max_chunk) { return (max_chunk + SEG_NEW - 1) / SEG_NEW; }
+
+// bytes of staging the compressor needs for n chunks of at most max_chunk bytes
+size_t stage_bytes_for(const lz4b200_ctx* c, size_t n, size_t max_chunk)
+{
+    if (segmented(c, max_chunk)) return n * segs_per_chunk(max_chunk) * slot_stride_for(SEG_BYTES);
+    return n * slot_stride_for(max_chunk);
+}
+
+int ensure_segmented(lz4b200_ctx* c, size_t n, size_t max_chunk)
+{
+    const size_t jobs = n * segs_per_chunk(max_chunk);
+    CU(c->seg64.ensure((2 * n + 3 * jobs + 8) * sizeof(u64)));
+    CU(c->seg32.ensure((6 * jobs + 8) * sizeof(u32)));
+    return 0;
+}
+
 int ensure_scratch(lz4b200_ctx* c, size_t n, size_t stage_bytes)
 {
     CU(c->uoff.ensure(n * sizeof(u64)));
@@ -161,8 +184,9 @@ Scratch scratch_at(lz4b200_ctx* c, size_t first_chunk, size_t stride, int slice)
     s.uoff = (u64*)c->uoff.p + first_chunk;
     s.coff = (u64*)c->coff.p + first_chunk;
     s.status = (u32*)c->status.p + first_chunk;
-    s.stage = c->stage.p ? (u8*)c->stage.p + first_chunk * stride : nullptr;
+    s.stage = c->stage.p ? (u8*)c->stage.p + first_chunk * stride : nullptr;   // `stride` = staging bytes per chunk
     s.ticket = (u32*)((u8*)c->scalars.p + SC_TICKETS) + slice;
+    s.first_chunk = first_chunk;
     return s;
 }
 
@@ -178,8 +202,37 @@ int compress_slice(lz4b200_ctx* c, const u8* d_in, const u64* d_usz, size_t n, s
     scan_sizes_kernel<<<1, SCAN_THREADS, 0, st>>>(in_scan, none, (u64)n);
     c->launches++;
 
+    SegArrays sa{};
+    const bool seg = segmented(c, max_chunk);
     time_begin(c, st);
-    if (c->compress_gen == 2 && c1_compress_supported(max_chunk)) {
+    if (seg) {
+        // chunks > 64 KiB: one job per 64 KiB segment on the tiled compressor, stitched afterwards (segmented.cuh)
+        const size_t per = segs_per_chunk(max_chunk);
+        const size_t jobs_max = n * per, job0 = s.first_chunk * per;
+        const size_t n_tot = c->seg_chunks, jobs_tot = n_tot * per;
+        u64* p64 = (u64*)c->seg64.p; u32* p32 = (u32*)c->seg32.p;
+        sa.jobs_per_chunk = p64 + s.first_chunk;
+        sa.job_base = p64 + n_tot + s.first_chunk;
+        sa.job_in_off = p64 + 2 * n_tot + job0;
+        sa.job_len = p64 + 2 * n_tot + jobs_tot + job0;
+        sa.job_csz = p64 + 2 * n_tot + 2 * jobs_tot + job0;
+        sa.n_jobs = (u64*)((u8*)c->scalars.p + SC_NJOBS) + (s.ticket - (u32*)((u8*)c->scalars.p + SC_TICKETS));
+        sa.job_tail_pos = p32 + job0;
+        sa.job_tail_len = p32 + jobs_tot + job0;
+        sa.job_rel = p32 + 2 * jobs_tot + job0;
+        sa.job_carry = p32 + 3 * jobs_tot + job0;
+        sa.job_chunk = p32 + 4 * jobs_tot + job0;
+        sa.job_hist = p32 + 5 * jobs_tot + job0;
+        const unsigned gb = (unsigned)((n + 255) / 256);
+        seg_count_kernel<<<gb, 256, 0, st>>>(d_usz, (u32)n, sa.jobs_per_chunk);
+        ScanJob js{ sa.jobs_per_chunk, sa.job_base, sa.n_jobs, nullptr };
+        scan_sizes_kernel<<<1, SCAN_THREADS, 0, st>>>(js, none, (u64)n);
+        seg_fill_kernel<<<gb, 256, 0, st>>>(d_usz, s.uoff, sa, (u32)n);
+        CU(c2_launch_compress(d_in, sa.job_in_off, sa.job_len, s.stage, slot_stride_for(SEG_BYTES), sa.job_csz,
+                              (u32)jobs_max, s.ticket, c->sm_count, st, sa.n_jobs, sa.job_tail_pos, sa.job_tail_len, sa.job_hist));
+        seg_stitch_size_kernel<<<gb, 256, 0, st>>>(sa, s.stage, slot_stride_for(SEG_BYTES), d_csz, (u32)n);
+        c->launches += 5;
+    } else if (c->compress_gen == 2 && c1_compress_supported(max_chunk)) {
         CU(c2_launch_compress(d_in, s.uoff, d_usz, s.stage, stride, d_csz, (u32)n, s.ticket, c->sm_count, st));
         c->launches++;
     } else if (c->compress_gen == 1 && c1_compress_supported(max_chunk)) {
@@ -203,8 +256,15 @@ int compress_slice(lz4b200_ctx* c, const u8* d_in, const u64* d_usz, size_t n, s
     scan_sizes_kernel<<<1, SCAN_THREADS, 0, st>>>(out_scan, none, (u64)n);
     c->launches++;
     if (record_after_scan) CU(cudaEventRecord(record_after_scan, st));
-    const unsigned grid = (unsigned)std::min<size_t>(n, (size_t)c->sm_count * 16);
-    compact_kernel<<<grid, COMPACT_THREADS, 0, st>>>(s.stage, stride, d_in, s.uoff, d_usz, d_csz, s.coff, d_out, (u32)n);
+    if (seg) {
+        const size_t jobs_max = n * segs_per_chunk(max_chunk);
+        const unsigned grid = (unsigned)std::min<size_t>(jobs_max, (size_t)c->sm_count * 16);
+        seg_stitch_copy_kernel<<<grid, SEG_COPY_THREADS, 0, st>>>(sa, s.stage, slot_stride_for(SEG_BYTES), d_in, s.uoff, d_usz,
+                                                                   d_csz, s.coff, d_out, (u32)jobs_max);
+    } else {
+        const unsigned grid = (unsigned)std::min<size_t>(n, (size_t)c->sm_count * 16);
+        compact_kernel<<<grid, COMPACT_THREADS, 0, st>>>(s.stage, stride, d_in, s.uoff, d_usz, d_csz, s.coff, d_out, (u32)n);
+    }
     c->launches++;
     CU(cudaGetLastError());
     return 0;
@@ -389,7 +449,7 @@ void lz4b200_destroy(lz4b200_ctx* c)
         if (c->ev_done[i]) cudaEventDestroy(c->ev_done[i]);
     }
     c->usz.release(); c->csz.release(); c->uoff.release(); c->coff.release();
-    c->scalars.release(); c->status.release(); c->stage.release();
+    c->scalars.release(); c->status.release(); c->stage.release(); c->seg64.release(); c->seg32.release();
     c->d_plain.release(); c->d_packed.release(); c->h_sizes.release(); c->prof.release();
     for (int i = 0; i < lz4b200_ctx::MAX_TIMED; i++) if (c->ev0[i]) { cudaEventDestroy(c->ev0[i]); cudaEventDestroy(c->ev1[i]); }
     delete c;
@@ -461,10 +521,11 @@ int lz4b200_compress_device(lz4b200_ctx* c, const void* d_in, const uint64_t* d_
     CU(cudaSetDevice(c->device));
     if (n == 0) { if (d_total_out) CU(cudaMemsetAsync(d_total_out, 0, sizeof(u64), st)); return 0; }
     if (int rc = check_batch(n, max_chunk)) return rc;
-    if (int rc = ensure_scratch(c, n, n * slot_stride_for(max_chunk))) return rc;
+    if (int rc = ensure_scratch(c, n, stage_bytes_for(c, n, max_chunk))) return rc;
+    if (segmented(c, max_chunk)) { if (int rc = ensure_segmented(c, n, max_chunk)) return rc; c->seg_chunks = n; }
     u64* total = d_total_out ? (u64*)d_total_out : (u64*)((u8*)c->scalars.p + SC_TOTAL);
     return compress_slice(c, (const u8*)d_in, (const u64*)d_chunk_sizes, n, max_chunk, (u8*)d_out,
-                          (u64*)d_compr_sizes, nullptr, total, scratch_at(c, 0, slot_stride_for(max_chunk), 0), st,
+                          (u64*)d_compr_sizes, nullptr, total, scratch_at(c, 0, stage_bytes_for(c, 1, max_chunk), 0), st,
                           nullptr, nullptr);
 }
 
@@ -504,11 +565,12 @@ int64_t lz4b200_compress_batch(lz4b200_ctx* c, const char* in, const size_t* chu
     if (int rc = check_batch(n, max_chunk)) return rc;
     maybe_register(c, in, total);
     maybe_register(c, out, out_capacity);
-    const size_t stride = slot_stride_for(max_chunk);
+    const size_t stride = stage_bytes_for(c, 1, max_chunk);          // staging bytes per chunk
     CU(c->usz.ensure(n * 8)); CU(c->csz.ensure(n * 8));
     CU(c->d_plain.ensure(total + 16));
-    CU(c->d_packed.ensure(total + total / 255 + 16 * n + 16));
+    CU(c->d_packed.ensure(total + total / 255 + 16 * (n + total / SEG_BYTES + 1) + 16));
     if (int rc = ensure_scratch(c, n, n * stride)) return rc;
+    if (segmented(c, max_chunk)) { if (int rc = ensure_segmented(c, n, max_chunk)) return rc; c->seg_chunks = n; }
     size_t first[lz4b200_ctx::MAX_SLICES + 1];
     const int K = plan_slices(c, chunk_sizes, n, total, false, first);
     if (int rc = ensure_events(c, K)) return rc;
