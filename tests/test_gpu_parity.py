@@ -218,3 +218,40 @@ def test_device_resident_roundtrip_256m(gpu_ctx, kernels):
         blk = packed[offs[i]:offs[i] + int(compr[i])]
         r, out = O.oracle_decompress(blk, chunk)
         assert r == chunk and zlib.crc32(out.tobytes()) == zlib.crc32(plain[i * chunk:(i + 1) * chunk].tobytes())
+
+
+def test_device_resident_roundtrip_5g_64bit_offsets(gpu_ctx):
+    """More than 4 GiB in one batch: every offset array is 64-bit (BASELINE configs[3] puts 8 GiB on the box).
+    Property check at full size: encode -> decode on the device, whole image compared on the device."""
+    import torch
+    gpu_ctx.set_option("kernels", "v4")
+    n = 5 << 30
+    chunk = 65536
+    host = torch.empty(n, dtype=torch.uint8)
+    L.corpus("mixed", n, seed=3, out=host.numpy())
+    d_in = host.cuda()
+    del host
+    n_chunks = n // chunk
+    d_cs = torch.full((n_chunks,), chunk, dtype=torch.int64, device="cuda")
+    d_out = torch.empty(L.get_compress_bound(n), dtype=torch.uint8, device="cuda")
+    d_compr = torch.empty(n_chunks, dtype=torch.int64, device="cuda")
+    d_total = torch.zeros(1, dtype=torch.int64, device="cuda")
+    s = torch.cuda.current_stream().cuda_stream
+    gpu_ctx.compress_device(d_in, d_cs, n_chunks, chunk, d_out, d_compr, d_total, s)
+    torch.cuda.synchronize()
+    total = int(d_total.item())
+    assert total > (4 << 30) * 0.55 and int(d_compr.sum().item()) == total
+    d_back = torch.zeros(n, dtype=torch.uint8, device="cuda")
+    d_bad = torch.zeros(1, dtype=torch.int32, device="cuda")
+    gpu_ctx.decompress_device(d_out, d_compr, d_cs, n_chunks, chunk, d_back, d_bad, s)
+    torch.cuda.synchronize()
+    assert int(d_bad.item()) == 0
+    assert torch.equal(d_back, d_in)
+    # the last chunks lie beyond the 4 GiB mark of both images: check a few against the oracle too
+    compr = d_compr.cpu().numpy().astype(np.uint64)
+    offs = np.concatenate([[0], np.cumsum(compr)[:-1]]).astype(np.int64)
+    for i in (n_chunks - 1, n_chunks - 7, 70000):
+        blk = d_out[int(offs[i]):int(offs[i]) + int(compr[i])].cpu().numpy()
+        plain = d_in[i * chunk:(i + 1) * chunk].cpu().numpy()
+        r, out = O.oracle_decompress(blk, chunk)
+        assert r == chunk and np.array_equal(out, plain)
