@@ -18,7 +18,21 @@ gens = sys.argv[4].split(",") if len(sys.argv) > 4 else ["v0", "v1"]
 ctx = L.Lz4B200(0)
 for kind in kinds:
     host = torch.empty(n, dtype=torch.uint8).pin_memory()
-    t0 = time.time(); L.corpus(kind, n, seed=2, out=host.numpy()); tg = time.time() - t0
+    t0 = time.time()
+    if kind.startswith("files:"):          # real data: concatenated files (shared objects of the image), repeated to n bytes
+        import glob
+        buf = bytearray()
+        for f in sorted(glob.glob(kind[6:])):
+            if os.path.isfile(f) and not os.path.islink(f):
+                buf += open(f, "rb").read()
+            if len(buf) >= n: break
+        a = np.frombuffer(bytes(buf), dtype=np.uint8)
+        reps = -(-n // len(a))
+        host.numpy()[:] = np.tile(a, reps)[:n] if reps > 1 else a[:n]
+        print("   real-file corpus:", len(a) >> 20, "MiB of distinct data", flush=True)
+    else:
+        L.corpus(kind, n, seed=2, out=host.numpy())
+    tg = time.time() - t0
     d_in = host.cuda()
     n_chunks = (n + chunk - 1) // chunk
     cs = L.chunk_list(n, chunk).astype(np.int64)
