@@ -25,7 +25,7 @@ for kind in kinds:
         for f in sorted(glob.glob(kind[6:])):
             if os.path.isfile(f) and not os.path.islink(f):
                 buf += open(f, "rb").read()
-            if len(buf) >= n: break
+            if len(buf) >= min(n, 128 << 20): break
         a = np.frombuffer(bytes(buf), dtype=np.uint8)
         reps = -(-n // len(a))
         host.numpy()[:] = np.tile(a, reps)[:n] if reps > 1 else a[:n]
@@ -78,6 +78,11 @@ for kind in kinds:
             print("   compress phases [load,match,parse,emit,final] %:", [round(100 * x / tot, 1) for x in pr[8:13]],
                   "cycles/chunk", tot // n_chunks, "parse rounds/tile %.2f" % (pr[13] / (n_chunks * 16)), flush=True)
         total = int(d_total.item())
+        if os.environ.get("REF"):
+            from tests import oracle_lib as O
+            m = min(n_chunks, (16 << 20) // chunk)
+            _, rc = O.oracle_chunked_compress(host.numpy()[:m * chunk], cs[:m].astype(np.uint64))
+            print("   size vs reference lz4 on the first %d chunks: %.4f" % (m, float(d_compr[:m].sum().item()) / float(rc.sum())), flush=True)
         ok = bool(torch.equal(d_back, d_in)) and int(d_bad.item()) == 0
         print(f"{kind} {n>>20}MiB chunk={chunk} {gen}: ratio={100*total/n:.2f}% "
               f"compress {n/res['compress']/1e6:.1f} GB/s ({res['compress']:.2f} ms) "
