@@ -430,7 +430,7 @@ inline cudaError_t c1_launch_mode(const u8* in, const u64* in_off, const u64* us
     return cudaGetLastError();
 }
 
-inline int& c1_mode() { static int m = 1; return m; }   // 0 match_any, 1 shuffle distances (default), 2 table only
+inline int& c1_mode() { static int m = 2; return m; }   // intra-warp candidates: 0 match_any, 1 shuffle distances, 2 none (default: the batch-local table covers them)
 
 inline cudaError_t c1_launch_compress(const u8* in, const u64* in_off, const u64* usz, u8* stage, u64 stride, u64* csz,
                                       u32 n, u32* ticket, u64* prof, int sm_count, size_t mc, cudaStream_t st)
