@@ -146,3 +146,66 @@ KATS = [
     ("literal-run-270", block(0xF0, 255, 0, bytes(range(256)) + bytes(range(14))), 270, bytes(range(256)) + bytes(range(14))),
     ("wrong-size", block(0xD0, b"abcdefghijklm"), 15, None),
 ]
+
+
+# ---- LZ4 frame container: oracle/lz4f_oracle.c and oracle/_ref/liblz4fref.so -------------------
+REF_FRAME_SO = os.path.join(ROOT, "oracle", "_ref", "liblz4fref.so")
+orc.oracle_xxh32.restype = C.c_uint32
+orc.oracle_xxh32.argtypes = [vp, C.c_size_t, C.c_uint32]
+orc.oracle_lz4f_bound.restype = C.c_size_t
+orc.oracle_lz4f_bound.argtypes = [C.c_size_t, C.c_int]
+orc.oracle_lz4f_compress.restype = C.c_size_t
+orc.oracle_lz4f_compress.argtypes = [vp, C.c_size_t, vp, C.c_size_t, C.c_int, C.c_int, C.c_int]
+orc.oracle_lz4f_decompress.restype = C.c_size_t
+orc.oracle_lz4f_decompress.argtypes = [vp, C.c_size_t, vp, C.c_size_t]
+
+reff = None
+if os.path.exists(REF_FRAME_SO):
+    reff = C.CDLL(REF_FRAME_SO)
+    reff.ref_lz4f_bound.restype = C.c_size_t
+    reff.ref_lz4f_bound.argtypes = [C.c_size_t, C.c_int, C.c_int, C.c_int]
+    reff.ref_lz4f_compress.restype = C.c_size_t
+    reff.ref_lz4f_compress.argtypes = [vp, C.c_size_t, vp, C.c_size_t] + [C.c_int] * 5
+    reff.ref_lz4f_decompress.restype = C.c_size_t
+    reff.ref_lz4f_decompress.argtypes = [vp, C.c_size_t, vp, C.c_size_t]
+    reff.XXH32.restype = C.c_uint32
+    reff.XXH32.argtypes = [vp, C.c_size_t, C.c_uint32]
+
+BAD = C.c_size_t(-1).value
+
+
+def _ptr(a):
+    return a.ctypes.data if len(a) else np.zeros(1, dtype=np.uint8).ctypes.data
+
+
+def oracle_frame_compress(data, block_id=4, content_checksum=0, with_content_size=0) -> np.ndarray:
+    data = _u8(data)
+    out = np.empty(orc.oracle_lz4f_bound(len(data), block_id), dtype=np.uint8)
+    n = orc.oracle_lz4f_compress(_ptr(data), len(data), out.ctypes.data, len(out), block_id, content_checksum,
+                                 with_content_size)
+    assert n > 0
+    return out[:n].copy()
+
+
+def oracle_frame_decompress(frame, cap):
+    frame = _u8(frame)
+    out = np.zeros(max(cap, 1), dtype=np.uint8)
+    r = orc.oracle_lz4f_decompress(_ptr(frame), len(frame), out.ctypes.data, cap)
+    return (r, out[:r]) if r != BAD else (BAD, out[:0])
+
+
+def ref_frame_compress(data, block_id=4, independent=1, content_checksum=0, block_checksum=0,
+                       with_content_size=0) -> np.ndarray:
+    data = _u8(data)
+    out = np.empty(reff.ref_lz4f_bound(len(data), block_id, content_checksum, block_checksum) + 64, dtype=np.uint8)
+    n = reff.ref_lz4f_compress(_ptr(data), len(data), out.ctypes.data, len(out), block_id, independent,
+                               content_checksum, block_checksum, with_content_size)
+    assert n > 0
+    return out[:n].copy()
+
+
+def ref_frame_decompress(frame, cap):
+    frame = _u8(frame)
+    out = np.zeros(max(cap, 1), dtype=np.uint8)
+    r = reff.ref_lz4f_decompress(_ptr(frame), len(frame), out.ctypes.data, cap)
+    return (r, out[:r]) if r != BAD else (BAD, out[:0])

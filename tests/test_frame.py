@@ -1,0 +1,75 @@
+"""CPU tests for the LZ4 frame checker: oracle/lz4f_oracle.c against the reference's own
+lz4frame.c + xxhash.c compiled into oracle/_ref/liblz4fref.so.  Frames are not expected to be byte-identical between
+implementations (the reference's frame encoder reuses its hash table across blocks), so the pin is: identical headers,
+both directions cross-decode, same accept/reject decisions on damaged frames."""
+import numpy as np
+import pytest
+
+import lzbench_b200 as L
+from tests import oracle_lib as O
+
+needs_ref = pytest.mark.skipif(O.reff is None, reason="oracle/_ref/liblz4fref.so not built (reference tree absent)")
+
+
+def test_xxh32_known_answers():
+    # published xxHash32 vectors: empty input seed 0, and "abc"
+    assert O.orc.oracle_xxh32(O._ptr(np.zeros(0, np.uint8)), 0, 0) == 0x02CC5D05
+    abc = np.frombuffer(b"abc", dtype=np.uint8)
+    assert O.orc.oracle_xxh32(abc.ctypes.data, 3, 0) == 0x32D153FF
+
+
+@needs_ref
+@pytest.mark.parametrize("n", [0, 1, 3, 4, 15, 16, 17, 31, 32, 33, 1000, 65537])
+def test_xxh32_matches_reference(n):
+    d = L.corpus("mixed", max(n, 1), seed=n)[:n]
+    for seed in (0, 1, 0x9E3779B1):
+        assert O.orc.oracle_xxh32(O._ptr(d), n, seed) == O.reff.XXH32(O._ptr(d), n, seed)
+
+
+SIZES = [0, 1, 11, 12, 13, 65535, 65536, 65537, 300000, (1 << 20) + 5]
+
+
+@needs_ref
+@pytest.mark.parametrize("block_id", [4, 5, 6, 7])
+@pytest.mark.parametrize("kind", ["mixed", "random", "zero"])
+def test_frames_cross_decode(block_id, kind):
+    for n in SIZES:
+        d = L.corpus(kind, max(n, 1), seed=3)[:n]
+        for cck, csz in ((0, 0), (1, 0), (0, 1), (1, 1)):
+            csz = csz if n else 0          # the reference API reads contentSize 0 as "unknown"
+            # LZ4F_compressFrame lowers the block size id to the smallest that holds the input (LZ4F_optimalBSID)
+            eff = next((b for b in range(4, block_id) if n <= 65536 << (2 * (b - 4))), block_id)
+            fo = O.oracle_frame_compress(d, eff, cck, csz)
+            fr = O.ref_frame_compress(d, block_id, 1, cck, 0, csz)
+            hl = 7 + 8 * csz
+            assert np.array_equal(fo[:hl], fr[:hl]), "frame headers differ"
+            for f in (fo, fr):
+                r, out = O.ref_frame_decompress(f, n + 16)
+                assert r == n and np.array_equal(out, d)
+                r, out = O.oracle_frame_decompress(f, n + 16)
+                assert r == n and np.array_equal(out, d)
+            # oracle frames are never larger than the reference's by more than rounding of the table reuse
+            assert len(fo) <= len(fr) * 1.01 + 16
+
+
+@needs_ref
+def test_block_checksum_frames_and_linked_blocks():
+    d = L.corpus("mixed", 300000, seed=8)
+    f = O.ref_frame_compress(d, 4, 1, 1, 1, 1)
+    r, out = O.oracle_frame_decompress(f, len(d))
+    assert r == len(d) and np.array_equal(out, d)
+    linked = O.ref_frame_compress(d, 4, 0)
+    assert O.oracle_frame_decompress(linked, len(d))[0] == O.BAD      # linked blocks are outside the chunked path
+
+
+@needs_ref
+def test_damaged_frames_rejected_by_both():
+    d = L.corpus("mixed", 200000, seed=2)
+    f = O.oracle_frame_compress(d, 4, 1, 1)
+    cases = []
+    for pos in (0, 4, 5, 6, 14, len(f) - 1, len(f) - 6):
+        g = f.copy(); g[pos] ^= 0x10; cases.append(g)
+    cases.append(f[:len(f) - 3]); cases.append(f[:20]); cases.append(f[:5])
+    for g in cases:
+        assert O.ref_frame_decompress(g, len(d) + 16)[0] == O.BAD
+        assert O.oracle_frame_decompress(g, len(d) + 16)[0] == O.BAD
