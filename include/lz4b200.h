@@ -133,6 +133,29 @@ int64_t lzbench_lz4_b200_compress_batch(const size_t* chunk_sizes, size_t n_chun
 int64_t lzbench_lz4_b200_decompress_batch(const size_t* chunk_sizes, const size_t* compr_sizes, size_t n_chunks,
                                           char* in, char* out, char* workmem);
 
+/* ---- LZ4 frame container around the chunked path -------------------
+ * A frame with independent blocks is the chunked hot path plus framing: magic, descriptor, one LE32 size word per
+ * block (bit 31 = stored uncompressed), end mark, optional xxHash32 checksums (lz4/lz4frame.h:119-186 for the types
+ * these arguments mirror).  Frames with linked blocks or a dictionary are outside the chunked path: rejected, -2. */
+#define LZ4B200_FRAME_CONTENT_CHECKSUM 1   /* LZ4F_contentChecksumEnabled, lz4/lz4frame.h:147; serial, computed on the host */
+#define LZ4B200_FRAME_BLOCK_CHECKSUM   2   /* LZ4F_blockChecksumEnabled,   lz4/lz4frame.h:154; per block, on the device   */
+#define LZ4B200_FRAME_CONTENT_SIZE     4   /* frameInfo.contentSize = n,   lz4/lz4frame.h:180                             */
+#define LZ4B200_FRAME_SKIP_CHECKSUMS   1   /* decompress flag: LZ4F_decompressOptions_t is not offered by 1.9.3; default verifies */
+
+/* Upper bound of a frame holding n bytes in blocks of id block_id (4..7 = 64 KiB, 256 KiB, 1 MiB, 4 MiB;
+ * LZ4F_blockSizeID_t, lz4/lz4frame.h:123-133).  Replaces LZ4F_compressFrameBound, lz4/lz4frame.h:215.  0 = bad id. */
+size_t  lz4b200_frame_bound(size_t n, int block_id);
+/* Replaces LZ4F_compressFrame (lz4/lz4frame.h:224, lz4/lz4frame.c:398-470) with blockMode = LZ4F_blockIndependent.
+ * Host buffers.  Returns the frame size, or < 0. */
+int64_t lz4b200_frame_compress(lz4b200_ctx* ctx, const char* in, size_t n, char* out, size_t out_capacity,
+                               int block_id, int flags);
+/* Replaces one complete LZ4F_decompress session (lz4/lz4frame.h:465, lz4/lz4frame.c:1372-1750) over one frame.
+ * Returns the decoded size; -1 malformed / checksum mismatch / does not fit, -2 valid but outside the chunked path. */
+int64_t lz4b200_frame_decompress(lz4b200_ctx* ctx, const char* in, size_t in_size, char* out, size_t out_capacity,
+                                 int flags);
+/* Replaces LZ4F_getFrameInfo(...).contentSize (lz4/lz4frame.h:430).  Host only.  -3 = the frame does not say. */
+int64_t lz4b200_frame_content_size(const char* in, size_t in_size);
+
 /* ---- synthetic corpora; host-side, deterministic ----------------------- */
 int lz4b200_corpus_fill(int kind, uint64_t seed, uint64_t offset, uint64_t len, uint8_t* out, int n_threads);
 

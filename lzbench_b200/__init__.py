@@ -12,6 +12,7 @@ from .codec import (  # noqa: F401
     compress_bound,
     corpus,
     get_compress_bound,
+    last_error,
     lib,
     lib_path,
     lzbench_compress,
@@ -19,6 +20,6 @@ from .codec import (  # noqa: F401
 )
 
 __all__ = [
-    "Lz4B200", "LibraryMissing", "chunk_list", "compress_bound", "corpus", "get_compress_bound",
+    "Lz4B200", "LibraryMissing", "chunk_list", "compress_bound", "corpus", "get_compress_bound", "last_error",
     "lib", "lib_path", "lzbench_compress", "lzbench_decompress",
 ]

@@ -67,12 +67,24 @@ def _load() -> C.CDLL:
     L.lzbench_lz4_b200_compress_batch.argtypes = [vp, sz, vp, vp, vp, sz, vp]
     L.lzbench_lz4_b200_decompress_batch.restype = i64
     L.lzbench_lz4_b200_decompress_batch.argtypes = [vp, vp, sz, vp, vp, vp]
+    L.lz4b200_frame_bound.restype = sz
+    L.lz4b200_frame_bound.argtypes = [sz, C.c_int]
+    L.lz4b200_frame_compress.restype = i64
+    L.lz4b200_frame_compress.argtypes = [vp, vp, sz, vp, sz, C.c_int, C.c_int]
+    L.lz4b200_frame_decompress.restype = i64
+    L.lz4b200_frame_decompress.argtypes = [vp, vp, sz, vp, sz, C.c_int]
+    L.lz4b200_frame_content_size.restype = i64
+    L.lz4b200_frame_content_size.argtypes = [vp, sz]
     L.lz4b200_corpus_fill.restype = C.c_int
     L.lz4b200_corpus_fill.argtypes = [C.c_int, u64, u64, u64, vp, C.c_int]
     return L
 
 
 lib = _load()
+
+
+FRAME_CONTENT_CHECKSUM, FRAME_BLOCK_CHECKSUM, FRAME_CONTENT_SIZE = 1, 2, 4     # include/lz4b200.h
+FRAME_SKIP_CHECKSUMS = 1
 
 
 def last_error() -> str:
@@ -198,6 +210,26 @@ class Lz4B200:
             outbuf = np.zeros(int(cs.sum()), dtype=np.uint8)
         r = lib.lz4b200_decompress_batch(self._h, _ptr(inbuf), zs.ctypes.data, cs.ctypes.data, len(cs), _ptr(outbuf))
         return outbuf, int(r)
+
+    # -- LZ4 frame container (lz4/lz4frame.h LZ4F_compressFrame / LZ4F_decompress; independent blocks) ------
+    def frame_compress(self, data, block_id: int = 4, content_checksum: bool = False, block_checksum: bool = False,
+                       content_size: bool = False, outbuf=None) -> np.ndarray:
+        n = data.nbytes if isinstance(data, np.ndarray) else data.numel()
+        if outbuf is None:
+            outbuf = np.empty(lib.lz4b200_frame_bound(n, block_id), dtype=np.uint8)
+        flags = (FRAME_CONTENT_CHECKSUM if content_checksum else 0) | (FRAME_BLOCK_CHECKSUM if block_checksum else 0) \
+            | (FRAME_CONTENT_SIZE if content_size else 0)
+        r = lib.lz4b200_frame_compress(self._h, _ptr(data) if n else None, n, _ptr(outbuf), outbuf.nbytes, block_id, flags)
+        if r < 0:
+            raise RuntimeError(f"lz4b200_frame_compress failed ({r}): {last_error()}")
+        return outbuf[:r]
+
+    def frame_decompress(self, frame, capacity: int, skip_checksums: bool = False):
+        """Returns (return code, output[:decoded size]); the code is negative for a rejected frame."""
+        out = np.zeros(max(capacity, 1), dtype=np.uint8)
+        r = lib.lz4b200_frame_decompress(self._h, _ptr(frame), frame.nbytes, _ptr(out), capacity,
+                                         FRAME_SKIP_CHECKSUMS if skip_checksums else 0)
+        return int(r), out[:max(int(r), 0)]
 
     # -- device-resident calls (torch CUDA tensors; asynchronous on `stream`) ---------------
     def compress_device(self, d_in, d_chunk_sizes, n_chunks: int, max_chunk: int, d_out, d_compr_sizes,

@@ -15,9 +15,11 @@
 #include "kernels_c1.cuh"
 #include "kernels_c2.cuh"
 #include "segmented.cuh"
+#include "frame.cuh"
 #include "staging.cuh"
 
 #include <algorithm>
+#include <vector>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -90,7 +92,7 @@ struct lz4b200_ctx {
     Reg regs[16] = {};
     int n_regs = 0;
     size_t seg_chunks = 0;              // chunk count the segmented job arrays are laid out for (current call)
-    static constexpr int NS = 4;        // compute/H2D streams of the host pipeline
+    static constexpr int NS = 8;        // compute/H2D streams of the host pipeline
     static constexpr int MAX_SLICES = 64;
     cudaStream_t streams[NS] = {};
     cudaStream_t d2h_stream = nullptr;
@@ -103,6 +105,7 @@ struct lz4b200_ctx {
     int n_timed = 0;
     // device-resident scratch shared by both directions
     DevBuf usz, csz, uoff, coff;        // u64[n_chunks]
+    DevBuf fsz, fhdr;                   // frame container: u64 framed block sizes / u32 block header words
     DevBuf scalars;                     // see Scalars below
     DevBuf status;                      // u32[n_chunks]
     DevBuf prof;                        // u64[16] phase-cycle counters (debug option "prof")
@@ -112,6 +115,8 @@ struct lz4b200_ctx {
     // buffers behind the host entry points
     DevBuf d_plain, d_packed;
     PinBuf h_sizes;                     // u64[2*n_chunks + MAX_SLICES + 2]
+    u64* h_mirror = nullptr;            // u64[MAX_SLICES] host-mapped: running totals the scan kernels store for the host
+    u64* d_mirror = nullptr;            // the same memory as the device addresses it
 };
 
 namespace {
@@ -119,6 +124,9 @@ namespace {
 // layout of ctx->scalars (8 KB)
 constexpr size_t SC_TOTAL = 0;          // u64  total compressed size (device entry point without caller buffer)
 constexpr size_t SC_BAD = 8;            // u32  malformed-chunk counter
+constexpr size_t SC_FBASE = 16;         // u64  frame container: position of the first block (= header bytes)
+constexpr size_t SC_FUNSUP = 24;        // u32  frame container: blocks the size rule cannot represent
+constexpr size_t SC_FCK = 28;           // u32  frame container: block checksum mismatches
 constexpr size_t SC_TICKETS = 256;      // u32[MAX_SLICES] work tickets, one per slice
 constexpr size_t SC_NJOBS = 1024;        // u64[MAX_SLICES] job counts of the segmented compressor, one per slice
 constexpr size_t SC_RUNNING = 4096;     // u64[MAX_SLICES] running compressed totals after each slice
@@ -127,6 +135,7 @@ constexpr size_t SC_BYTES = 8192;
 // per-slice view of the scratch arrays: slices of one host call run concurrently on different streams
 struct Scratch {
     u64* uoff; u64* coff; u32* status; u8* stage; u32* ticket;
+    u64* fsz;                          // frame mode only
     size_t first_chunk;                // slices of one call own disjoint regions of the per-chunk / per-job arrays
 };
 
@@ -186,6 +195,7 @@ Scratch scratch_at(lz4b200_ctx* c, size_t first_chunk, size_t stride, int slice)
     s.status = (u32*)c->status.p + first_chunk;
     s.stage = c->stage.p ? (u8*)c->stage.p + first_chunk * stride : nullptr;   // `stride` = staging bytes per chunk
     s.ticket = (u32*)((u8*)c->scalars.p + SC_TICKETS) + slice;
+    s.fsz = c->fsz.p ? (u64*)c->fsz.p + first_chunk : nullptr;
     s.first_chunk = first_chunk;
     return s;
 }
@@ -195,8 +205,9 @@ Scratch scratch_at(lz4b200_ctx* c, size_t first_chunk, size_t stride, int slice)
 // (0 if null), compact into d_out at those absolute offsets, write the running total to *d_total.
 int compress_slice(lz4b200_ctx* c, const u8* d_in, const u64* d_usz, size_t n, size_t max_chunk, u8* d_out,
                    u64* d_csz, const u64* base, u64* d_total, const Scratch& s, cudaStream_t st,
-                   cudaEvent_t wait_before_scan, cudaEvent_t record_after_scan)
+                   cudaEvent_t wait_before_scan, cudaEvent_t record_after_scan, int frame = 0, u64* mirror = nullptr)
 {
+    // frame: 0 = lzbench's contiguous image, 1 = LZ4 frame blocks (LE32 size word before each), 2 = 1 + block checksums
     const size_t stride = slot_stride_for(max_chunk);
     ScanJob in_scan{ d_usz, s.uoff, nullptr, nullptr }, none{ nullptr, nullptr, nullptr, nullptr };
     scan_sizes_kernel<<<1, SCAN_THREADS, 0, st>>>(in_scan, none, (u64)n);
@@ -251,11 +262,20 @@ int compress_slice(lz4b200_ctx* c, const u8* d_in, const u64* d_usz, size_t n, s
         c->launches++;
     }
     time_end(c, st);
+    const unsigned gn = (unsigned)((n + 255) / 256);
+    if (frame) {
+        frame_sizes_kernel<<<gn, 256, 0, st>>>(d_csz, d_usz, s.fsz, (u32)n, frame == 2 ? 4u : 0u);
+        c->launches++;
+    }
     if (wait_before_scan) CU(cudaStreamWaitEvent(st, wait_before_scan, 0));
-    ScanJob out_scan{ d_csz, s.coff, d_total, base };
+    ScanJob out_scan{ frame ? s.fsz : d_csz, s.coff, d_total, base, mirror };
     scan_sizes_kernel<<<1, SCAN_THREADS, 0, st>>>(out_scan, none, (u64)n);
     c->launches++;
     if (record_after_scan) CU(cudaEventRecord(record_after_scan, st));
+    if (frame) {
+        frame_headers_kernel<<<gn, 256, 0, st>>>(d_out, s.coff, d_csz, d_usz, (u32)n);
+        c->launches++;
+    }
     if (seg) {
         const size_t jobs_max = n * segs_per_chunk(max_chunk);
         const unsigned grid = (unsigned)std::min<size_t>(jobs_max, (size_t)c->sm_count * 16);
@@ -266,16 +286,27 @@ int compress_slice(lz4b200_ctx* c, const u8* d_in, const u64* d_usz, size_t n, s
         compact_kernel<<<grid, COMPACT_THREADS, 0, st>>>(s.stage, stride, d_in, s.uoff, d_usz, d_csz, s.coff, d_out, (u32)n);
     }
     c->launches++;
+    if (frame == 2) {
+        frame_block_xxh_kernel<<<(unsigned)((n + 63) / 64), 64, 0, st>>>(d_out, s.coff, d_csz, (u32)n, 0, nullptr);
+        c->launches++;
+    }
     CU(cudaGetLastError());
     return 0;
 }
 
 int decompress_slice(lz4b200_ctx* c, const u8* d_in, const u64* d_csz, const u64* d_usz, size_t n, size_t max_chunk,
-                     u8* d_out, u32* d_bad, const Scratch& s, cudaStream_t st, int team = 0)
+                     u8* d_out, u32* d_bad, const Scratch& s_in, cudaStream_t st, int team = 0,
+                     const u64* given_coff = nullptr)
 {
-    ScanJob a{ d_csz, s.coff, nullptr, nullptr }, b{ d_usz, s.uoff, nullptr, nullptr };
-    scan_sizes_kernel<<<2, SCAN_THREADS, 0, st>>>(a, b, (u64)n);
-    c->launches++;
+    // given_coff: the chunks are not contiguous in d_in (frame blocks have a size word between them); the caller has
+    // filled their positions and s.uoff (absolute output offsets) itself.
+    Scratch s = s_in;
+    if (given_coff) s.coff = const_cast<u64*>(given_coff);
+    else {
+        ScanJob a{ d_csz, s.coff, nullptr, nullptr }, b{ d_usz, s.uoff, nullptr, nullptr };
+        scan_sizes_kernel<<<2, SCAN_THREADS, 0, st>>>(a, b, (u64)n);
+        c->launches++;
+    }
     time_begin(c, st);
     // team width: with few chunks per launch the run time is the latency of one chunk's chain, which is shorter
     // on wider teams, and wider teams also spread few chunks over more SMs
@@ -334,17 +365,16 @@ int check_batch(size_t n, size_t max_chunk)
 }
 
 // Cut chunks [0,n) into K contiguous slices of roughly equal uncompressed size; first[k] = first chunk of slice k.
-// Equal slices by bytes.  Slice counts measured with scripts/e2e_probe.py (1 GiB, pinned buffers): decompress is
-// best with 16 slices (the PCIe copy of the output is the bottleneck as soon as the first slice is decoded, and
-// small slices run on wider teams with a shorter per-chunk latency), compress with 8; a geometric ramp at the
-// small end was tried and was no better.
+// Equal slices by bytes.  Slice counts measured with scripts/e2e_probe.py (1 GiB, pinned buffers, 8 streams): both
+// directions are best with 16 slices (the PCIe copy of the larger side is the bottleneck as soon as the first slice
+// is through, and a slice's kernels last as long as one chunk's serial chain however few chunks it holds, so
+// several slices must be in flight at once); a geometric ramp at the small end was tried and was no better.
 int plan_slices(const lz4b200_ctx* c, const size_t* chunk_sizes, size_t n, size_t total, bool decompress,
                 size_t* first /* K+1 */)
 {
     int K = c->slices;
     if (K <= 0) {
-        K = total >= (512u << 20) ? 8 : (total >= (128u << 20) ? 4 : (total >= (32u << 20) ? 2 : 1));
-        if (decompress && K >= 4) K *= 2;
+        K = total >= (512u << 20) ? 16 : (total >= (128u << 20) ? 8 : (total >= (32u << 20) ? 2 : 1));
     }
     if (K > lz4b200_ctx::MAX_SLICES) K = lz4b200_ctx::MAX_SLICES;
     if ((size_t)K > n) K = (int)n;
@@ -431,6 +461,10 @@ int lz4b200_create(int device, size_t max_total_bytes, size_t max_chunk_bytes, l
         c->h_sizes.ensure((2 * n + lz4b200_ctx::MAX_SLICES + 2) * 8);
     }
     if (ensure_scratch(c, 1, 0) != 0) { lz4b200_destroy(c); return -2; }
+    if (cudaHostAlloc((void**)&c->h_mirror, lz4b200_ctx::MAX_SLICES * sizeof(u64), cudaHostAllocMapped) != cudaSuccess ||
+        cudaHostGetDevicePointer((void**)&c->d_mirror, c->h_mirror, 0) != cudaSuccess) {
+        lz4b200_destroy(c); return fail(-2, "cudaHostAlloc (mapped) failed");
+    }
     *out = c;
     return 0;
 }
@@ -451,6 +485,8 @@ void lz4b200_destroy(lz4b200_ctx* c)
     c->usz.release(); c->csz.release(); c->uoff.release(); c->coff.release();
     c->scalars.release(); c->status.release(); c->stage.release(); c->seg64.release(); c->seg32.release();
     c->d_plain.release(); c->d_packed.release(); c->h_sizes.release(); c->prof.release();
+    c->fsz.release(); c->fhdr.release();
+    if (c->h_mirror) cudaFreeHost(c->h_mirror);
     for (int i = 0; i < lz4b200_ctx::MAX_TIMED; i++) if (c->ev0[i]) { cudaEventDestroy(c->ev0[i]); cudaEventDestroy(c->ev1[i]); }
     delete c;
 }
@@ -550,8 +586,11 @@ int lz4b200_decompress_device(lz4b200_ctx* c, const void* d_in, const uint64_t* 
 // the compressed size of the slices before it, which exists only on the device: the output scan of slice
 // k starts from the running total slice k-1 left in device memory (event-ordered), and the host learns
 // the totals one slice behind to place the D2H copies.
-int64_t lz4b200_compress_batch(lz4b200_ctx* c, const char* in, const size_t* chunk_sizes, size_t n,
-                               char* out, size_t out_capacity, size_t* compr_sizes)
+// frame_hdr > 0: write LZ4 frame blocks starting at out + frame_hdr instead of lzbench's contiguous image, and keep
+// frame_tail bytes of out_capacity free behind them (end mark, content checksum); the caller writes header and tail.
+static int64_t compress_batch_impl(lz4b200_ctx* c, const char* in, const size_t* chunk_sizes, size_t n,
+                                   char* out, size_t out_capacity, size_t* compr_sizes,
+                                   size_t frame_hdr, size_t frame_tail, bool block_checksum)
 {
     if (!c) return fail(-1, "null ctx");
     if (n == 0) return 0;
@@ -560,7 +599,6 @@ int64_t lz4b200_compress_batch(lz4b200_ctx* c, const char* in, const size_t* chu
     size_t total = 0, max_chunk = 0;
     CU(c->h_sizes.ensure((2 * n + lz4b200_ctx::MAX_SLICES + 2) * sizeof(u64)));
     u64* h = (u64*)c->h_sizes.p;
-    u64* h_tot = h + 2 * n;
     for (size_t i = 0; i < n; i++) { h[i] = chunk_sizes[i]; total += chunk_sizes[i]; max_chunk = std::max(max_chunk, chunk_sizes[i]); }
     if (int rc = check_batch(n, max_chunk)) return rc;
     maybe_register(c, in, total);
@@ -568,7 +606,8 @@ int64_t lz4b200_compress_batch(lz4b200_ctx* c, const char* in, const size_t* chu
     const size_t stride = stage_bytes_for(c, 1, max_chunk);          // staging bytes per chunk
     CU(c->usz.ensure(n * 8)); CU(c->csz.ensure(n * 8));
     CU(c->d_plain.ensure(total + 16));
-    CU(c->d_packed.ensure(total + total / 255 + 16 * (n + total / SEG_BYTES + 1) + 16));
+    CU(c->d_packed.ensure(total + total / 255 + 16 * (n + total / SEG_BYTES + 1) + 16 + (frame_hdr ? 8 * n + 32 : 0)));
+    if (frame_hdr) CU(c->fsz.ensure(n * 8));
     if (int rc = ensure_scratch(c, n, n * stride)) return rc;
     if (segmented(c, max_chunk)) { if (int rc = ensure_segmented(c, n, max_chunk)) return rc; c->seg_chunks = n; }
     size_t first[lz4b200_ctx::MAX_SLICES + 1];
@@ -576,6 +615,13 @@ int64_t lz4b200_compress_batch(lz4b200_ctx* c, const char* in, const size_t* chu
     if (int rc = ensure_events(c, K)) return rc;
 
     u64* running = (u64*)((u8*)c->scalars.p + SC_RUNNING);
+    u64* fbase = (u64*)((u8*)c->scalars.p + SC_FBASE);
+    const int frame = frame_hdr ? (block_checksum ? 2 : 1) : 0;
+    if (frame) {                                          // header is at most 19 bytes: the low byte carries it
+        CU(cudaMemsetAsync(fbase, 0, 8, c->streams[0]));
+        CU(cudaMemsetAsync(fbase, (int)frame_hdr, 1, c->streams[0]));
+    }
+    const size_t usable = out_capacity >= frame_tail ? out_capacity - frame_tail : 0;
     CU(cudaMemcpyAsync(c->usz.p, h, n * 8, cudaMemcpyHostToDevice, c->streams[0]));
     CU(cudaEventRecord(c->ev_sizes, c->streams[0]));
     size_t in_off = 0;
@@ -587,20 +633,20 @@ int64_t lz4b200_compress_batch(lz4b200_ctx* c, const char* in, const size_t* chu
         CU(cudaStreamWaitEvent(st, c->ev_sizes, 0));
         CU(cudaMemcpyAsync((u8*)c->d_plain.p + in_off, in + in_off, bytes, cudaMemcpyHostToDevice, st));
         int rc = compress_slice(c, (const u8*)c->d_plain.p + in_off, (const u64*)c->usz.p + f, m, max_chunk,
-                                (u8*)c->d_packed.p, (u64*)c->csz.p + f, k ? running + (k - 1) : nullptr, running + k,
-                                scratch_at(c, f, stride, k), st, k ? c->ev_scan[k - 1] : nullptr, c->ev_scan[k]);
+                                (u8*)c->d_packed.p, (u64*)c->csz.p + f, k ? running + (k - 1) : (frame ? fbase : nullptr), running + k,
+                                scratch_at(c, f, stride, k), st, k ? c->ev_scan[k - 1] : nullptr, c->ev_scan[k], frame, c->d_mirror + k);
         if (rc) { cudaDeviceSynchronize(); return rc; }
-        CU(cudaMemcpyAsync(h_tot + k, running + k, 8, cudaMemcpyDeviceToHost, st));
-        CU(cudaMemcpyAsync(h + n + f, (u64*)c->csz.p + f, m * 8, cudaMemcpyDeviceToHost, st));
+        // no device-to-host copies on this stream: they would queue behind the bulk copies of earlier slices on the
+        // copy engine and hold back this stream's next H2D; totals reach the host through the mapped mirror
         CU(cudaEventRecord(c->ev_done[k], st));
         in_off += bytes;
     }
-    u64 base = 0;
+    u64 base = frame_hdr;
     bool overflow = false;
     for (int k = 0; k < K; k++) {
         CU(cudaEventSynchronize(c->ev_done[k]));
-        const u64 end = h_tot[k];
-        if (end > out_capacity) { overflow = true; break; }
+        const u64 end = ((volatile u64*)c->h_mirror)[k];
+        if (end > usable) { overflow = true; break; }
         CU(cudaMemcpyAsync(out + base, (u8*)c->d_packed.p + base, end - base, cudaMemcpyDeviceToHost, c->d2h_stream));
         base = end;
     }
@@ -609,9 +655,16 @@ int64_t lz4b200_compress_batch(lz4b200_ctx* c, const char* in, const size_t* chu
         fail(0, "compressed image exceeds output capacity %zu", out_capacity);
         return 0;                                        // _lzbench/lzbench.cpp:286
     }
+    CU(cudaMemcpyAsync(h + n, c->csz.p, n * 8, cudaMemcpyDeviceToHost, c->d2h_stream));
     CU(cudaStreamSynchronize(c->d2h_stream));
     for (size_t i = 0; i < n; i++) compr_sizes[i] = (size_t)h[n + i];
     return (int64_t)base;
+}
+
+int64_t lz4b200_compress_batch(lz4b200_ctx* c, const char* in, const size_t* chunk_sizes, size_t n,
+                               char* out, size_t out_capacity, size_t* compr_sizes)
+{
+    return compress_batch_impl(c, in, chunk_sizes, n, out, out_capacity, compr_sizes, 0, 0, false);
 }
 
 int64_t lz4b200_decompress_batch(lz4b200_ctx* c, const char* in, const size_t* compr_sizes,
@@ -668,4 +721,173 @@ int64_t lz4b200_decompress_batch(lz4b200_ctx* c, const char* in, const size_t* c
     return (int64_t)total;
 }
 
+// ---- LZ4 frame container (frame.cuh) -----------------------------------------------------------
+
+size_t lz4b200_frame_bound(size_t n, int block_id)
+{
+    const size_t b = frame_block_bytes(block_id);
+    if (!b) return 0;
+    return 19 + (n / b + 1) * 8 + n + 8;                   // header, per block size word + checksum, end mark, content checksum
+}
+
+// One frame, independent blocks of frame_block_bytes(block_id): what LZ4F_compressFrame produces with
+// blockMode = LZ4F_blockIndependent (lz4/lz4frame.c:398-470), except that every block is compressed with a fresh
+// table (as lzbench's chunks are) and the block size id is used as given.
+int64_t lz4b200_frame_compress(lz4b200_ctx* c, const char* in, size_t n, char* out, size_t out_capacity,
+                               int block_id, int flags)
+{
+    if (!c) return fail(-1, "null ctx");
+    const size_t bsz = frame_block_bytes(block_id);
+    if (!bsz) return fail(-1, "block_id must be 4..7 (64 KiB .. 4 MiB)");
+    if (!out || (n && !in)) return fail(-1, "null argument");
+    const bool cck = flags & LZ4B200_FRAME_CONTENT_CHECKSUM, bck = flags & LZ4B200_FRAME_BLOCK_CHECKSUM,
+               wsz = flags & LZ4B200_FRAME_CONTENT_SIZE;
+    const size_t tail = 4 + (cck ? 4 : 0);
+    if (out_capacity < 19 + tail) return fail(-1, "output capacity too small for a frame");
+    u8 hdr[19];
+    const size_t hl = frame_write_header(hdr, block_id, bck, cck, wsz, n);
+    int64_t end = (int64_t)hl;
+    if (n) {
+        const size_t nb = (n + bsz - 1) / bsz;
+        std::vector<size_t> sizes(nb, bsz), csz(nb);
+        sizes[nb - 1] = n - (nb - 1) * bsz;
+        // the block pipeline runs asynchronously up to its first host wait; the content checksum (one serial
+        // xxHash32 chain over the input, host only) would ideally overlap it, but correctness first: it is a
+        // separate pass, and only when the caller asks for it
+        end = compress_batch_impl(c, in, sizes.data(), nb, out, out_capacity, csz.data(), hl, tail, bck);
+        if (end <= 0) return end ? end : fail(-1, "frame exceeds output capacity %zu", out_capacity);
+    }
+    memcpy(out, hdr, hl);
+    h_wr32((u8*)out + end, 0);                             // end mark, lz4frame.c:917
+    end += 4;
+    if (cck) { h_wr32((u8*)out + end, xxh32_host(in, n)); end += 4; }
+    return end;
+}
+
+int64_t lz4b200_frame_content_size(const char* in, size_t in_size)
+{
+    FrameInfo fi; const char* why = "";
+    if (!in) return fail(-1, "null argument");
+    if (int rc = frame_read_header((const u8*)in, in_size, &fi, &why)) return fail(rc, "%s", why);
+    return fi.has_content_size ? (int64_t)fi.content_size : -3;
+}
+
+// LZ4F_decompress for a whole frame with independent blocks (lz4/lz4frame.c:1372-1750).  The host walks the block
+// size words (one 4-byte read per block); everything that touches block payloads runs on the device: checksum of
+// every block, a size pass (the frame does not store decoded sizes), and the chunk decoders.
+int64_t lz4b200_frame_decompress(lz4b200_ctx* c, const char* in, size_t in_size, char* out, size_t out_capacity, int flags)
+{
+    if (!c) return fail(-1, "null ctx");
+    if (!in || (!out && out_capacity)) return fail(-1, "null argument");
+    CU(cudaSetDevice(c->device));
+    FrameInfo fi; const char* why = "";
+    const u8* src = (const u8*)in;
+    if (int rc = frame_read_header(src, in_size, &fi, &why)) return fail(rc, "%s", why);
+    const bool verify = !(flags & LZ4B200_FRAME_SKIP_CHECKSUMS);
+    const size_t bx = fi.block_checksum ? 4 : 0;
+    // pass 1 (host): block positions
+    std::vector<u64> pos; std::vector<u32> words;
+    size_t ip = fi.header_bytes;
+    for (;;) {
+        if (ip + 4 > in_size) return fail(-1, "truncated frame (block header)");
+        const u32 w = h_rd32(src + ip);
+        ip += 4;
+        if (w == 0) break;
+        const size_t sz = w & ~F_RAW;
+        if (sz > fi.block_max) return fail(-1, "block larger than the frame's block size");
+        if (ip + sz + bx > in_size) return fail(-1, "truncated frame (block payload)");
+        pos.push_back(ip); words.push_back(w);
+        ip += sz + bx;
+    }
+    u32 stored_cck = 0;
+    if (fi.content_checksum) {
+        if (ip + 4 > in_size) return fail(-1, "truncated frame (content checksum)");
+        stored_cck = h_rd32(src + ip);
+        ip += 4;
+    }
+    const size_t frame_bytes = ip, n = pos.size();
+    if (n == 0) {
+        if (fi.has_content_size && fi.content_size != 0) return fail(-1, "content size mismatch");
+        if (fi.content_checksum && verify && stored_cck != xxh32_host(out, 0)) return fail(-1, "content checksum mismatch");
+        return 0;
+    }
+    if (int rc = check_batch(n, fi.block_max)) return rc;
+    maybe_register(c, in, frame_bytes);
+    maybe_register(c, out, out_capacity);
+    CU(c->h_sizes.ensure((2 * n + lz4b200_ctx::MAX_SLICES + 4) * sizeof(u64)));
+    u64* h = (u64*)c->h_sizes.p;
+    u32* hw = (u32*)(h + n);
+    u64* h_tot = h + 2 * n;
+    std::vector<size_t> weight(n);
+    for (size_t i = 0; i < n; i++) { h[i] = pos[i]; hw[i] = words[i]; weight[i] = (words[i] & ~F_RAW) + 4 + bx; }
+    // decoded bytes are bounded by blocks x block size, and anything beyond the caller's buffer is an error anyway
+    const size_t limit = std::min<u64>((u64)n * fi.block_max, out_capacity);
+    CU(c->usz.ensure(n * 8)); CU(c->csz.ensure(n * 8)); CU(c->fsz.ensure(n * 8)); CU(c->fhdr.ensure(n * 4));
+    CU(c->d_packed.ensure(frame_bytes + 16));
+    CU(c->d_plain.ensure(limit + 16));
+    if (int rc = ensure_scratch(c, n, 0)) return rc;
+    size_t first[lz4b200_ctx::MAX_SLICES + 1];
+    const int K = plan_slices(c, weight.data(), n, frame_bytes, true, first);
+    if (int rc = ensure_events(c, K)) return rc;
+    u8* sc = (u8*)c->scalars.p;
+    u32 *d_bad = (u32*)(sc + SC_BAD), *d_unsup = (u32*)(sc + SC_FUNSUP), *d_ck = (u32*)(sc + SC_FCK);
+    u64* running = (u64*)(sc + SC_RUNNING);
+    u64* d_pos = (u64*)c->fsz.p;
+    CU(cudaMemsetAsync(sc, 0, 32, c->streams[0]));
+    CU(cudaMemcpyAsync(d_pos, h, n * 8, cudaMemcpyHostToDevice, c->streams[0]));
+    CU(cudaMemcpyAsync(c->fhdr.p, hw, n * 4, cudaMemcpyHostToDevice, c->streams[0]));
+    CU(cudaEventRecord(c->ev_sizes, c->streams[0]));
+    // slices of blocks flow through H2D -> size pass -> scan (from the previous slice's running total) -> decode;
+    // the host learns each slice's output range one event behind and issues the D2H copies on their own stream
+    for (int k = 0; k < K; k++) {
+        cudaStream_t st = c->streams[k % lz4b200_ctx::NS];
+        const size_t f = first[k], m = first[k + 1] - first[k];
+        const size_t lo = pos[f] - 4, hi = pos[f + m - 1] + (words[f + m - 1] & ~F_RAW) + bx;
+        CU(cudaStreamWaitEvent(st, c->ev_sizes, 0));
+        CU(cudaMemcpyAsync((u8*)c->d_packed.p + lo, in + lo, hi - lo, cudaMemcpyHostToDevice, st));
+        u64 *csz_k = (u64*)c->csz.p + f, *usz_k = (u64*)c->usz.p + f;
+        frame_block_sizes_kernel<<<(unsigned)((m + FS_WARPS - 1) / FS_WARPS), FS_WARPS * 32, 0, st>>>(
+            (const u8*)c->d_packed.p, frame_bytes, d_pos + f, (const u32*)c->fhdr.p + f, csz_k, usz_k, (u32)m,
+            (u32)fi.block_max, d_unsup);
+        c->launches++;
+        if (fi.block_checksum && verify) {
+            frame_block_xxh_kernel<<<(unsigned)((m + 63) / 64), 64, 0, st>>>((u8*)c->d_packed.p, d_pos + f, csz_k, (u32)m, 1, d_ck);
+            c->launches++;
+        }
+        const Scratch sk = scratch_at(c, f, 0, k);
+        if (k) CU(cudaStreamWaitEvent(st, c->ev_scan[k - 1], 0));
+        ScanJob tot{ usz_k, sk.uoff, running + k, k ? running + (k - 1) : nullptr, c->d_mirror + k }, none{ nullptr, nullptr, nullptr, nullptr, nullptr };
+        scan_sizes_kernel<<<1, SCAN_THREADS, 0, st>>>(tot, none, (u64)m);
+        CU(cudaEventRecord(c->ev_scan[k], st));
+        frame_guard_kernel<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(usz_k, csz_k, (u32)m, running + k, (u64)limit);
+        c->launches += 2;
+        int rc = decompress_slice(c, (const u8*)c->d_packed.p, csz_k, usz_k, m, fi.block_max, (u8*)c->d_plain.p, d_bad,
+                                  sk, st, 0, d_pos + f);
+        if (rc) { cudaDeviceSynchronize(); return rc; }
+        CU(cudaEventRecord(c->ev_done[k], st));
+    }
+    u64 total = 0;
+    for (int k = 0; k < K; k++) {
+        CU(cudaEventSynchronize(c->ev_done[k]));
+        const u64 end = ((volatile u64*)c->h_mirror)[k];
+        if (end > out_capacity) {
+            CU(cudaDeviceSynchronize());
+            return fail(-1, "decoded size exceeds output capacity %zu", out_capacity);
+        }
+        CU(cudaMemcpyAsync(out + total, (u8*)c->d_plain.p + total, end - total, cudaMemcpyDeviceToHost, c->d2h_stream));
+        total = end;
+    }
+    u32* h_res = (u32*)(h_tot + K);                          // bad, (pad), unsupported, checksum mismatches
+    CU(cudaMemcpyAsync(h_res, d_bad, 4, cudaMemcpyDeviceToHost, c->d2h_stream));
+    CU(cudaMemcpyAsync(h_res + 2, d_unsup, 8, cudaMemcpyDeviceToHost, c->d2h_stream));
+    CU(cudaStreamSynchronize(c->d2h_stream));
+    if (h_res[3]) return fail(-1, "%u block checksum mismatch(es)", h_res[3]);
+    if (h_res[2]) return fail(-2, "%u compressed block(s) not smaller than their content: not representable on the chunked path", h_res[2]);
+    if (h_res[0]) { fail(-1, "%u malformed block(s)", h_res[0]); return -(int64_t)h_res[0]; }
+    if (fi.has_content_size && fi.content_size != total) return fail(-1, "content size mismatch");
+    if (fi.content_checksum && verify && stored_cck != xxh32_host(out, total)) return fail(-1, "content checksum mismatch");
+    return (int64_t)total;
+}
+
 }  // extern "C"
+

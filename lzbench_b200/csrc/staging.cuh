@@ -12,7 +12,7 @@ constexpr int SCAN_THREADS = 1024;
 // Exclusive prefix sum of up to two u64 arrays in one launch (blockIdx.x picks the array).
 // One CTA per array: every thread owns a contiguous run, the run totals are scanned in
 // shared memory, then the run is rewritten.  n is at most a few million (8 GiB / 4 KiB).
-struct ScanJob { const u64* sizes; u64* offsets; u64* total; const u64* base; };   // offsets start at *base (0 if null); *total = *base + sum
+struct ScanJob { const u64* sizes; u64* offsets; u64* total; const u64* base; u64* mirror; };   // offsets start at *base (0 if null); *total = *base + sum, also stored to *mirror (host-mapped memory: the host reads it after an event, no copy engine involved)
 
 __global__ void __launch_bounds__(SCAN_THREADS) scan_sizes_kernel(ScanJob j0, ScanJob j1, u64 n)
 {
@@ -50,6 +50,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_sizes_kernel(ScanJob j0, Sc
     u64 base = start + x - local + (warp ? warp_sums[warp - 1] : 0);
     for (u64 i = lo; i < hi; i++) { u64 s = j.sizes[i]; j.offsets[i] = base; base += s; }
     if (tid == 0 && j.total) *j.total = start + carry;
+    if (tid == 0 && j.mirror) *j.mirror = start + carry;
 }
 
 // Compaction: one CTA per chunk (grid-stride).  Source is the chunk's staging slot, or the
