@@ -12,6 +12,7 @@
 #include "kernels_v2.cuh"
 #include "kernels_v3.cuh"
 #include "kernels_v4.cuh"
+#include "kernels_v5.cuh"
 #include "kernels_c1.cuh"
 #include "kernels_c2.cuh"
 #include "segmented.cuh"
@@ -312,11 +313,15 @@ int decompress_slice(lz4b200_ctx* c, const u8* d_in, const u64* d_csz, const u64
     // on wider teams, and wider teams also spread few chunks over more SMs
     if (!team) team = c->team;
     if (!team) team = n * 4 <= (size_t)c->sm_count * 32 ? 32 : (n * 2 <= (size_t)c->sm_count * 32 ? 16 : 8);
-    if (c->kernel_gen == 4 && team != 32) {
+    if (c->kernel_gen == 5 && team != 32) {
+        CU(v5_launch_decompress(team, d_in, s.coff, d_csz, s.uoff, d_usz, d_out, s.status, d_bad, (u32)n,
+                                s.ticket, c->sm_count, st));
+        c->launches += 1;
+    } else if (c->kernel_gen == 4 && team != 32) {
         CU(v4_launch_decompress(team, d_in, s.coff, d_csz, s.uoff, d_usz, d_out, s.status, d_bad, (u32)n,
                                 s.ticket, c->sm_count, st));
         c->launches += 1;
-    } else if (c->kernel_gen == 4) {                    // one warp per chunk: the v2 kernel at T = 32
+    } else if (c->kernel_gen >= 4) {                    // one warp per chunk: the v2 kernel at T = 32
         CU(v2_launch_decompress(32, d_in, s.coff, d_csz, s.uoff, d_usz, d_out, s.status, d_bad, (u32)n,
                                 s.ticket, c->sm_count, st));
         c->launches += 1;
@@ -443,6 +448,8 @@ int lz4b200_create(int device, size_t max_total_bytes, size_t max_chunk_bytes, l
     if (gen && !strcmp(gen, "v1")) c->kernel_gen = 1;
     if (gen && !strcmp(gen, "v2")) c->kernel_gen = 2;
     if (gen && !strcmp(gen, "v3")) c->kernel_gen = 3;
+    if (gen && !strcmp(gen, "v4")) c->kernel_gen = 4;
+    if (gen && !strcmp(gen, "v5")) c->kernel_gen = 5;
     for (int i = 0; i < lz4b200_ctx::NS; i++) {
         cudaError_t e = cudaStreamCreateWithFlags(&c->streams[i], cudaStreamNonBlocking);
         if (e != cudaSuccess) { lz4b200_destroy(c); return fail(-2, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
@@ -502,6 +509,7 @@ int lz4b200_set_option(lz4b200_ctx* c, const char* key, const char* value)
         if (!strcmp(value, "v2")) { c->kernel_gen = 2; c->compress_gen = 2; return 0; }
         if (!strcmp(value, "v3")) { c->kernel_gen = 3; c->compress_gen = 2; return 0; }
         if (!strcmp(value, "v4")) { c->kernel_gen = 4; c->compress_gen = 2; return 0; }
+        if (!strcmp(value, "v5")) { c->kernel_gen = 5; c->compress_gen = 2; return 0; }
     }
     if (!strcmp(key, "compress")) {
         if (!strcmp(value, "v0")) { c->compress_gen = 0; return 0; }
