@@ -34,7 +34,7 @@ struct V5Params {
     u32* status; u32* bad_chunks; u32* ticket; u32 n_chunks;
 };
 // loop-carried state of one lane, handed to the cold function through local memory
-struct V5State { u8* dst; u32 ip, op, tok, pm_len, op_safe, ip_safe, rem; bool busy, exhausted, fastable; };
+struct V5State { u8* dst; u32 ip, op, tok, pm_len, op_safe, ip_safe, rem; bool busy, exhausted, fastable; u32 lrem; };
 
 // request stream segment g (16*T bytes at the 16-aligned base of the chunk + g*SEG) into its ring slot
 template <u32 T>
@@ -81,9 +81,10 @@ __device__ __noinline__ bool v5_cold(V5State& S, const bool f, const V5Params& P
             } else if (ip >= clen) {
                 err = ST_TOKEN_OOB; finished = true;
             } else {
-                const u32 token = S.tok; ip++;
-                u64 len = token >> 4;
-                if (len == RUN_MASK) {
+                const u32 token = S.tok;
+                u64 len = S.lrem;                       // mid literal run (common path, 16 bytes per iteration): ip is at the next literal
+                if (len == 0) { ip++; len = token >> 4; }
+                if (S.lrem == 0 && len == RUN_MASK) {
                     if (ip + RUN_MASK >= clen) err = ST_LITLEN_OOB;
                     else {
                         u32 s;
@@ -176,7 +177,7 @@ __device__ __noinline__ bool v5_cold(V5State& S, const bool f, const V5Params& P
         else {
             src = P.in + P.in_off[c]; clen = (u32)P.csz[c];
             dst = P.out + P.out_off[c]; n = (u32)P.usz[c];
-            op = 0; busy = true; S.pm_len = 0; S.rem = 0;
+            op = 0; busy = true; S.pm_len = 0; S.rem = 0; S.lrem = 0;
             const bool raw = clen == n;
             fastable = !raw && n >= 32 && clen >= 24;
             S.op_safe = fastable ? n - MFLIMIT : 0;        // match end + MFLIMIT <= n (non-last sequence, lz4/lz4.c:1990,:2139)
@@ -211,6 +212,7 @@ __device__ __noinline__ bool v5_cold(V5State& S, const bool f, const V5Params& P
         if (any2) cp_async_wait<0>(); else cp_async_wait<1>();
         __syncwarp();                                      // ring and ts visible to the whole team
     }
+    if (restart) S.lrem = 0;
     if (restart) S.tok = fastable ? (u32)ring[ip & (RING - 1)] : (ip < clen ? (u32)__ldg(src + ip) : 0u);
 #undef V5_RD
     return false;
@@ -245,30 +247,39 @@ decompress_v5_kernel(const __grid_constant__ V5Params P)
     u32 op_safe = 0, ip_safe = 0;                      // fast path allowed while op + L <= op_safe and ip + L <= ip_safe
     bool fastable = false;                             // busy, not a raw chunk, big enough for the fast path at all
     u32 rem = 0, roff = 0;                             // long match in progress: bytes still owed; offset of the last fast match
+    u32 lrem = 0;                                      // long literal run in progress: literals still owed before the token's match; ip is at the next one
 
     for (;;) {
         // ---- A: decode the current token of every team (warp level, no branches) ----
         // A match longer than 18 bytes (token nibble 15 + one length byte) is executed 18 bytes per iteration:
         // `rem` bytes are still owed at offset `roff`; while rem != 0 the (already read) next token waits.
-        const bool cont = rem != 0;
+        // A literal run of 15..269 bytes (token nibble 15 + one length byte, 3 % of the sequences of the bench corpus
+        // and almost all of what used to leave the common path) is executed 16 bytes per iteration in the same way:
+        // `lrem` literals are still owed and ip has moved to the next of them; the token (and its match) waits.
+        const bool cont = rem != 0, lcont = lrem != 0;
         const u32 Lt = tok >> 4, M = tok & ML_MASK;
-        const u32 L = cont ? 0u : Lt;
+        const u32 e1 = ring[(ip + 1) & (RING - 1)];      // literal length byte, if the nibble is 15
+        const bool lext = Lt == RUN_MASK;
+        const u32 LL = lcont ? lrem : (lext ? 15u + e1 : Lt);                    // literals owed before the match
+        const u32 lpos = ip + (lcont ? 0u : (lext ? 2u : 1u));                    // stream position of the next literal
+        const bool lonly = !cont && LL > 16u;                                      // this iteration: 16 literals, nothing else
+        const u32 L = cont ? 0u : (lonly ? 16u : LL);
         const u32 cpy = op + L;
-        const u32 rp = ip + 1;                          // ring position of the byte after the token
-        const u32 lo = ring[(rp + Lt) & (RING - 1)];
-        const u32 hi = ring[(rp + Lt + 1) & (RING - 1)];
-        const u32 e = ring[(rp + Lt + 2) & (RING - 1)];  // length byte, if the nibble is 15
+        const u32 mp = lpos + LL;                        // stream position of the match offset
+        const u32 lo = ring[mp & (RING - 1)];
+        const u32 hi = ring[(mp + 1) & (RING - 1)];
+        const u32 e = ring[(mp + 2) & (RING - 1)];       // match length byte, if the nibble is 15
         const bool ext = M == ML_MASK;
         const u32 off = cont ? roff : (lo | (hi << 8));
         const u32 ml_total = cont ? rem : (ext ? 19u + e : M + MINMATCH);
-        const u32 ml = ml_total < 18u ? ml_total : 18u;                           // this iteration's part
-        const u32 nip = ip + Lt + 3 + (ext ? 1u : 0u);
-        // fast: short literal run, non-overlapping match of <= 273 bytes, valid offset, far enough from both ends
-        // of the block that (a) this is not the last sequence (lz4/lz4.c:1990), (b) the match ends 12 bytes
+        const u32 ml = lonly ? 0u : (ml_total < 18u ? ml_total : 18u);          // this iteration's part
+        const u32 nip = mp + 2 + (ext ? 1u : 0u);
+        // fast: literal run of at most 269 bytes, non-overlapping match of <= 273 bytes, valid offset, far enough from
+        // both ends of the block that (a) this is not the last sequence (lz4/lz4.c:1990), (b) the match ends 12 bytes
         // before the end and (c) the next token and its 17 bytes are inside the chunk
-        const bool f = fastable && (cont || (tok < 0xF0u && (!ext || (Lt <= 13u && e != 255u)) &&
-                                            cpy + ml_total <= op_safe && ip + Lt <= ip_safe && off <= cpy)) &&
-                       off >= ml;
+        const bool f = fastable && (cont || lcont || ((!lext || e1 != 255u) && mp <= ip_safe)) &&
+                       (lonly ? cpy + 16u <= op_safe
+                              : ((cont || ((!ext || e != 255u) && cpy + ml_total <= op_safe && off <= cpy)) && off >= ml));
 
         // ---- B: store the previous part's match bytes (loaded one iteration ago), every lane its own positions ----
         {
@@ -292,16 +303,17 @@ decompress_v5_kernel(const __grid_constant__ V5Params P)
             const u32 lim = f ? L : 0u;
             #pragma unroll
             for (u32 k = 0; k < NX; k++) {
-                const u32 val = ring[(rp + i0 + k * T) & (RING - 1)];
+                const u32 val = ring[(lpos + i0 + k * T) & (RING - 1)];
                 if (i0 + k * T < lim) p[k * T] = (u8)val;
             }
         }
         // ---- R: keep the ring two segments ahead of where the next iteration reads.  Placed here because no global
         //      load is outstanding at this point (B consumed last iteration's), so the barrier drains nothing.
         {
-            const bool need = f && !cont && (nip / SEG != ip / SEG);        // the read position enters a new segment
+            const u32 ip2 = lonly ? lpos + 16u : nip;                       // where ip goes if this iteration is fast
+            const bool need = f && !cont && (ip2 / SEG != ip / SEG);        // the read position enters a new segment
             if (__any_sync(FULL, need)) {
-                if (need) v5_request<T>(ring, ts.src, ts.clen, nip / SEG + 2, j);
+                if (need) v5_request<T>(ring, ts.src, ts.clen, ip2 / SEG + 2, j);
                 cp_async_commit();
                 cp_async_wait<1>();                     // everything but the segment just requested has landed
                 __syncwarp();
@@ -316,26 +328,27 @@ decompress_v5_kernel(const __grid_constant__ V5Params P)
             #pragma unroll
             for (u32 k = 0; k < NM; k++) pvb[k] = t0 + k * T < ml ? (u32)q[k * T] : 0u;
             pm_len = ml;
-            if (!cont) {
+            if (lonly) { ip = lpos + 16u; lrem = LL - 16u; }
+            else if (!cont) {
                 tok = ring[nip & (RING - 1)];
-                ip = nip; roff = off;
+                ip = nip; roff = off; lrem = 0;
             }
-            rem = ml_total - ml;
+            if (!lonly) rem = ml_total - ml;
             op = cpy + ml;
         }
 
         // ---- everything else, behind one vote and one call ----
         if (!__any_sync(FULL, (busy && !f) || (!busy && !exhausted))) continue;
-        V5State S{ dst, ip, op, tok, pm_len, op_safe, ip_safe, rem, busy, exhausted, fastable };
+        V5State S{ dst, ip, op, tok, pm_len, op_safe, ip_safe, rem, busy, exhausted, fastable, lrem };
         const bool done = v5_cold<T>(S, f, P, ring, ts);
         dst = S.dst; ip = S.ip; op = S.op; tok = S.tok; pm_len = S.pm_len; op_safe = S.op_safe; ip_safe = S.ip_safe;
-        rem = S.rem; busy = S.busy; exhausted = S.exhausted; fastable = S.fastable;
+        rem = S.rem; busy = S.busy; exhausted = S.exhausted; fastable = S.fastable; lrem = S.lrem;
         if (done) break;
         {   // Consume every restored value HERE.  They come back through local memory, and ptxas gives those loads
             // the same scoreboard as the match-source loads of the loop: without a consumer on this side of the
             // back edge, the first instruction of the loop waits for that scoreboard in EVERY iteration, i.e. for
             // the match loads it is supposed to overlap (seen as 25 % of all stall samples on the loop head).
-            const u32 sink = ip ^ op ^ tok ^ pm_len ^ op_safe ^ ip_safe ^ rem ^ (u32)reinterpret_cast<uintptr_t>(dst) ^
+            const u32 sink = ip ^ op ^ tok ^ pm_len ^ op_safe ^ ip_safe ^ rem ^ lrem ^ (u32)reinterpret_cast<uintptr_t>(dst) ^
                              (u32)(reinterpret_cast<uintptr_t>(dst) >> 32) ^ (u32)busy ^ (u32)exhausted ^ (u32)fastable;
             if (sink == 0x9E3779B9u) v5_sink = sink;            // harmless; a real use of the values that ptxas cannot drop
         }

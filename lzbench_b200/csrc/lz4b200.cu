@@ -13,6 +13,7 @@
 #include "kernels_v3.cuh"
 #include "kernels_v4.cuh"
 #include "kernels_v5.cuh"
+#include "kernels_v6.cuh"
 #include "kernels_c1.cuh"
 #include "kernels_c2.cuh"
 #include "segmented.cuh"
@@ -313,7 +314,11 @@ int decompress_slice(lz4b200_ctx* c, const u8* d_in, const u64* d_csz, const u64
     // on wider teams, and wider teams also spread few chunks over more SMs
     if (!team) team = c->team;
     if (!team) team = n * 4 <= (size_t)c->sm_count * 32 ? 32 : (n * 2 <= (size_t)c->sm_count * 32 ? 16 : 8);
-    if (c->kernel_gen == 5 && team != 32) {
+    if (c->kernel_gen == 6 && team != 32) {
+        CU(v6_launch_decompress(team, d_in, s.coff, d_csz, s.uoff, d_usz, d_out, s.status, d_bad, (u32)n,
+                                s.ticket, c->sm_count, st));
+        c->launches += 1;
+    } else if (c->kernel_gen == 5 && team != 32) {
         CU(v5_launch_decompress(team, d_in, s.coff, d_csz, s.uoff, d_usz, d_out, s.status, d_bad, (u32)n,
                                 s.ticket, c->sm_count, st));
         c->launches += 1;
@@ -450,6 +455,7 @@ int lz4b200_create(int device, size_t max_total_bytes, size_t max_chunk_bytes, l
     if (gen && !strcmp(gen, "v3")) c->kernel_gen = 3;
     if (gen && !strcmp(gen, "v4")) c->kernel_gen = 4;
     if (gen && !strcmp(gen, "v5")) c->kernel_gen = 5;
+    if (gen && !strcmp(gen, "v6")) c->kernel_gen = 6;
     for (int i = 0; i < lz4b200_ctx::NS; i++) {
         cudaError_t e = cudaStreamCreateWithFlags(&c->streams[i], cudaStreamNonBlocking);
         if (e != cudaSuccess) { lz4b200_destroy(c); return fail(-2, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
@@ -510,6 +516,7 @@ int lz4b200_set_option(lz4b200_ctx* c, const char* key, const char* value)
         if (!strcmp(value, "v3")) { c->kernel_gen = 3; c->compress_gen = 2; return 0; }
         if (!strcmp(value, "v4")) { c->kernel_gen = 4; c->compress_gen = 2; return 0; }
         if (!strcmp(value, "v5")) { c->kernel_gen = 5; c->compress_gen = 2; return 0; }
+        if (!strcmp(value, "v6")) { c->kernel_gen = 6; c->compress_gen = 2; return 0; }
     }
     if (!strcmp(key, "compress")) {
         if (!strcmp(value, "v0")) { c->compress_gen = 0; return 0; }
@@ -520,6 +527,10 @@ int lz4b200_set_option(lz4b200_ctx* c, const char* key, const char* value)
     if (!strcmp(key, "team")) {
         int t = atoi(value);
         if (t == 0 || t == 4 || t == 8 || t == 16 || t == 32) { c->team = t; return 0; }
+    }
+    if (!strcmp(key, "depth")) {                        // v6: iterations between fetching and storing a match part
+        int d = atoi(value);
+        if (d >= 2 && d <= 4) { v6_depth() = d; return 0; }
     }
     if (!strcmp(key, "host_register")) { c->host_register = value[0] == '1'; return 0; }
     if (!strcmp(key, "slices")) {

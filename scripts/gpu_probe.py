@@ -48,7 +48,9 @@ for kind in kinds:
             ctx.set_option("kernels", "v4"); ctx.set_option("compress", "v" + gen[1])
         elif gen.startswith("c1m"):
             ctx.set_option("kernels", "v2"); ctx.set_option("c1mode", gen[3:])
-        elif gen.startswith("v4t") or gen.startswith("v5t"):
+        elif gen.startswith("v6d"):                      # v6d<depth>t<team>
+            ctx.set_option("kernels", "v6"); ctx.set_option("depth", gen[3]); ctx.set_option("team", gen[5:])
+        elif gen.startswith("v4t") or gen.startswith("v5t") or gen.startswith("v6t"):
             ctx.set_option("kernels", gen[:2]); ctx.set_option("team", gen[3:])
         elif gen.startswith("v3t"):
             ctx.set_option("kernels", "v3"); ctx.set_option("team", gen[3:])

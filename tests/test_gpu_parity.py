@@ -42,7 +42,7 @@ def check_gpu_blocks_with_reference(data, packed, compr, cs):
         off_u += n
 
 
-@pytest.mark.parametrize("kernels", ["v0", "v1", "v2", "v3", "v4", "v5"])
+@pytest.mark.parametrize("kernels", ["v0", "v1", "v2", "v3", "v4", "v5", "v6"])
 @pytest.mark.parametrize("chunk", [4096, 65536, 100000, 1 << 20])
 @pytest.mark.parametrize("kind,seed", CORPORA)
 def test_compress_cross_decodes_and_ratio(gpu_ctx, kernels, chunk, kind, seed):
@@ -57,7 +57,7 @@ def test_compress_cross_decodes_and_ratio(gpu_ctx, kernels, chunk, kind, seed):
     assert total <= RATIO_TOLERANCE * int(ref_compr.sum()) + 64, (total, int(ref_compr.sum()))
 
 
-@pytest.mark.parametrize("kernels", ["v0", "v1", "v2", "v3", "v4", "v5"])
+@pytest.mark.parametrize("kernels", ["v0", "v1", "v2", "v3", "v4", "v5", "v6"])
 @pytest.mark.parametrize("chunk", [4096, 65536, 100000, 1 << 20])
 @pytest.mark.parametrize("kind,seed", CORPORA)
 def test_decompress_reference_blocks_bit_exact(gpu_ctx, kernels, chunk, kind, seed):
@@ -71,7 +71,7 @@ def test_decompress_reference_blocks_bit_exact(gpu_ctx, kernels, chunk, kind, se
     assert np.array_equal(out, data)
 
 
-@pytest.mark.parametrize("kernels", ["v0", "v1", "v2", "v3", "v4", "v5"])
+@pytest.mark.parametrize("kernels", ["v0", "v1", "v2", "v3", "v4", "v5", "v6"])
 def test_small_and_ragged_chunks(gpu_ctx, kernels):
     gpu_ctx.set_option("kernels", kernels)
     rng = np.random.default_rng(5)
@@ -91,7 +91,7 @@ def test_small_and_ragged_chunks(gpu_ctx, kernels):
         assert r == n and np.array_equal(out, data)
 
 
-@pytest.mark.parametrize("kernels", ["v0", "v1", "v2", "v3", "v4", "v5"])
+@pytest.mark.parametrize("kernels", ["v0", "v1", "v2", "v3", "v4", "v5", "v6"])
 def test_raw_stored_chunks(gpu_ctx, kernels):
     """compr_sizes[i] == chunk_sizes[i] means raw bytes (_lzbench/lzbench.cpp:311-315)."""
     gpu_ctx.set_option("kernels", kernels)
@@ -107,7 +107,7 @@ def test_raw_stored_chunks(gpu_ctx, kernels):
     assert r == len(data) and np.array_equal(out, data)
 
 
-@pytest.mark.parametrize("kernels", ["v0", "v1", "v2", "v3", "v4", "v5"])
+@pytest.mark.parametrize("kernels", ["v0", "v1", "v2", "v3", "v4", "v5", "v6"])
 def test_kat_table_on_gpu(gpu_ctx, kernels):
     gpu_ctx.set_option("kernels", kernels)
     for name, blk, n, expect in O.KATS:
@@ -121,7 +121,7 @@ def test_kat_table_on_gpu(gpu_ctx, kernels):
             assert out.tobytes() == expect, name
 
 
-@pytest.mark.parametrize("kernels", ["v0", "v1", "v2", "v3", "v4", "v5"])
+@pytest.mark.parametrize("kernels", ["v0", "v1", "v2", "v3", "v4", "v5", "v6"])
 def test_corrupted_blocks_never_crash_and_match_oracle(gpu_ctx, kernels):
     gpu_ctx.set_option("kernels", kernels)
     rng = np.random.default_rng(13)
@@ -148,7 +148,7 @@ def test_corrupted_blocks_never_crash_and_match_oracle(gpu_ctx, kernels):
             assert np.array_equal(out[i], ref_out), i
 
 
-@pytest.mark.parametrize("kernels", ["v0", "v1", "v2", "v3", "v4", "v5"])
+@pytest.mark.parametrize("kernels", ["v0", "v1", "v2", "v3", "v4", "v5", "v6"])
 def test_plugin_signature_wrappers(gpu_ctx, kernels):
     """lzbench_lz4_b200_{init,compress,decompress,deinit}: the unpatched-harness path, one chunk per call."""
     wm = L.lib.lzbench_lz4_b200_init(65536, 0, 0)
@@ -182,7 +182,7 @@ def test_output_capacity_rule(gpu_ctx):
     assert total == 0
 
 
-@pytest.mark.parametrize("kernels", ["v0", "v1", "v2", "v3", "v4", "v5"])
+@pytest.mark.parametrize("kernels", ["v0", "v1", "v2", "v3", "v4", "v5", "v6"])
 def test_device_resident_roundtrip_256m(gpu_ctx, kernels):
     """Full-size property test: encode -> decode on the device, compare CRC of the whole image."""
     import torch
