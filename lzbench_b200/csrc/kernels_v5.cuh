@@ -277,9 +277,14 @@ decompress_v5_kernel(const __grid_constant__ V5Params P)
         // fast: literal run of at most 269 bytes, non-overlapping match of <= 273 bytes, valid offset, far enough from
         // both ends of the block that (a) this is not the last sequence (lz4/lz4.c:1990), (b) the match ends 12 bytes
         // before the end and (c) the next token and its 17 bytes are inside the chunk
-        const bool f = fastable && (cont || lcont || ((!lext || e1 != 255u) && mp <= ip_safe)) &&
-                       (lonly ? cpy + 16u <= op_safe
-                              : ((cont || ((!ext || e != 255u) && cpy + ml_total <= op_safe && off <= cpy)) && off >= ml));
+        // (bitwise on purpose: with && / || ptxas builds a divergent branch tree here and parks the wait for the
+        //  in-flight match loads on its first branch, 20 % of all stall samples)
+        const u32 c_cont = cont, c_lcont = lcont, c_lonly = lonly;
+        const u32 c_hdr = c_cont | c_lcont | ((u32)(!lext | (e1 != 255u)) & (u32)(mp <= ip_safe));
+        const u32 c_lit = (u32)(cpy + 16u <= op_safe);
+        const u32 c_mat = (c_cont | ((u32)(!ext | (e != 255u)) & (u32)(cpy + ml_total <= op_safe) & (u32)(off <= cpy))) &
+                          (u32)(off >= ml);
+        const bool f = ((u32)fastable & c_hdr & (c_lonly ? c_lit : c_mat)) != 0;
 
         // ---- B: store the previous part's match bytes (loaded one iteration ago), every lane its own positions ----
         {
