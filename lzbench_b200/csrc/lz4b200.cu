@@ -85,7 +85,7 @@ struct PinBuf {
 struct lz4b200_ctx {
     int device = 0;
     int sm_count = 148;
-    int kernel_gen = 4;                 // decode: 0 warp per chunk, 1 CTA tile (TMA), 2 sub-warp teams, 3 + mapped lanes / pipelined match, 4 + warp-uniform fast path (default)
+    int kernel_gen = 5;                 // decode: 0 warp per chunk, 1 CTA tile (TMA), 2 sub-warp teams, 3 + mapped lanes / pipelined match, 4 + warp-uniform fast path, 5 + compressed stream through a cp.async ring, long literal runs on the common path (default), 6 = 5 with cp.async-staged deep match pipeline (experiment)
     int compress_gen = 2;               // compress: 0 warp per chunk, 1 CTA per chunk (parallel match finder + speculative parse), 2 = 1 with the phases on two warp groups (default)
     int team = 0;                       // lanes per chunk for the team decoders: 8 / 16 / 32, 0 = by batch size
     int slices = 0;                     // host entry points: number of pipeline slices (0 = automatic)
@@ -313,7 +313,10 @@ int decompress_slice(lz4b200_ctx* c, const u8* d_in, const u64* d_csz, const u64
     // team width: with few chunks per launch the run time is the latency of one chunk's chain, which is shorter
     // on wider teams, and wider teams also spread few chunks over more SMs
     if (!team) team = c->team;
-    if (!team) team = n * 4 <= (size_t)c->sm_count * 32 ? 32 : (n * 2 <= (size_t)c->sm_count * 32 ? 16 : 8);
+    if (!team) {
+        if (c->kernel_gen >= 5) team = n * 2 <= (size_t)c->sm_count * 32 ? 16 : 8;      // measured (scripts/team_probe.py): 1024 chunks take 2.0 ms on 16 lanes, 2.6 on 8, 3.7 on a warp (v2)
+        else team = n * 4 <= (size_t)c->sm_count * 32 ? 32 : (n * 2 <= (size_t)c->sm_count * 32 ? 16 : 8);
+    }
     if (c->kernel_gen == 6 && team != 32) {
         CU(v6_launch_decompress(team, d_in, s.coff, d_csz, s.uoff, d_usz, d_out, s.status, d_bad, (u32)n,
                                 s.ticket, c->sm_count, st));
