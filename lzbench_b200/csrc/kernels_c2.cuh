@@ -102,7 +102,7 @@ __global__ void __launch_bounds__(C2_THREADS, 2)
 compress_c2_kernel(const u8* __restrict__ in, const u64* __restrict__ in_off, const u64* __restrict__ usz,
                    u8* __restrict__ stage, u64 slot_stride, u64* __restrict__ csz, u32 n_chunks_arg, u32* ticket,
                    const u64* __restrict__ n_dev, u32* __restrict__ tail_pos, u32* __restrict__ tail_len,
-                   const u32* __restrict__ hist_arr)
+                   const u32* __restrict__ hist_arr, u64* __restrict__ prof)
 {
     // segmented mode (segmented.cuh): the job count lives in device memory and every job also reports where its
     // last_literals record starts and how many literals it holds
@@ -141,6 +141,7 @@ compress_c2_kernel(const u8* __restrict__ in, const u64* __restrict__ in_off, co
         const u32 n = (u32)usz[chunk];
         u8* dst = stage + (u64)chunk * slot_stride;
 
+        const long long pt0 = prof ? clock64() : 0;
         // ---- stage the chunk (TMA bulk copy of the aligned interior, edges by hand), clear the table ----
         const u32 head = (u32)(reinterpret_cast<uintptr_t>(src) & 15);
         u8* const s_in = s_in_raw + head;
@@ -163,6 +164,7 @@ compress_c2_kernel(const u8* __restrict__ in, const u64* __restrict__ in_off, co
             if (bulk) { mbar_wait(s_bar, phase); phase ^= 1; }
         }
         __syncthreads();
+        if (prof && tid == 0) atomicAdd((unsigned long long*)&prof[5], (unsigned long long)(clock64() - pt0));
 
         if (n >= MIN_LENGTH) {
             // a job that is not the end of its chunk (segmented mode, bit 31 of hist_arr) may match right up to its
@@ -177,7 +179,9 @@ compress_c2_kernel(const u8* __restrict__ in, const u64* __restrict__ in_off, co
                     const u32 t0 = t * C1_TILE, buf = t & 1;
                     u16* const mo = s_moff2 + buf * C1_TILE;
                     u32* const bi = s_bits2 + buf * (C1_TILE / 32);
+                    const long long a0 = prof ? clock64() : 0;
                     if (t >= 2) c2_bar_sync(3, buf);          // group B has released this buffer
+                    const long long a1 = prof ? clock64() : 0;
                     // ---- M: match finding over the tile, 256 positions per batch ----
                     for (u32 b = 0; b < C1_TILE; b += C2_GROUP) {
                         const u32 p = t0 + b + gtid;
@@ -223,6 +227,7 @@ compress_c2_kernel(const u8* __restrict__ in, const u64* __restrict__ in_off, co
                     }
 
                     __threadfence_block();
+                    if (prof && gtid == 0) { atomicAdd((unsigned long long*)&prof[1], (unsigned long long)(a1 - a0)); atomicAdd((unsigned long long*)&prof[0], (unsigned long long)(clock64() - a1)); }
                     c2_bar_arrive(1, buf);                    // tile t is ready
                 }
             } else {
@@ -233,7 +238,9 @@ compress_c2_kernel(const u8* __restrict__ in, const u64* __restrict__ in_off, co
                     const u32 t0 = t * C1_TILE, buf = t & 1;
                     const u16* const mo = s_moff2 + buf * C1_TILE;
                     const u32* const bi = s_bits2 + buf * (C1_TILE / 32);
+                    const long long b0 = prof ? clock64() : 0;
                     c2_bar_sync(1, buf);                      // wait for tile t
+                    const long long b1 = prof ? clock64() : 0;
                     // ---- P: greedy parse by speculative windows ----
                     const u32 wstart = t0 + gtid * C1_WP, wend = wstart + C1_WP;
                     const u32 wbits = (bi[gtid >> 1] >> ((gtid & 1) * 16)) & 0xFFFFu;
@@ -320,10 +327,12 @@ compress_c2_kernel(const u8* __restrict__ in, const u64* __restrict__ in_off, co
                         if (!C2_OR_B(need_walk) || round > 2 * C1_NW + 8) {   // the round limit cannot trigger; keeps the loop finite
                             // converged: chain state after the tile = exit of the furthest producer
                             if (total_key) { const u32 x = s_exit[total_key & 0xFFFFu]; if (x > cur) cur = x; }
+                            if (prof && gtid == 0) atomicAdd((unsigned long long*)&prof[7], (unsigned long long)(round + 1));
                             break;
                         }
                     }
 
+                    const long long b2 = prof ? clock64() : 0;
                     // ---- E: emit the tile's sequences ----
                     // pass 1: backward catch-up (lz4/lz4.c:1019) and encoded size per window
                     u32 enc = 0;
@@ -375,6 +384,7 @@ compress_c2_kernel(const u8* __restrict__ in, const u64* __restrict__ in_off, co
                     }
                     op += tile_bytes;
                     C2_BAR_B();
+                    if (prof && gtid == 0) { atomicAdd((unsigned long long*)&prof[2], (unsigned long long)(b1 - b0)); atomicAdd((unsigned long long*)&prof[3], (unsigned long long)(b2 - b1)); atomicAdd((unsigned long long*)&prof[4], (unsigned long long)(clock64() - b2)); }
                     if (t + 2 < n_tiles) c2_bar_arrive(3, buf);   // buffer free for tile t + 2
                 }
                 if (gtid == 0) { s_misc[4] = cur; s_misc[5] = op; }
@@ -403,7 +413,7 @@ compress_c2_kernel(const u8* __restrict__ in, const u64* __restrict__ in_off, co
 
 template <int MODE>
 inline cudaError_t c2_launch_mode(const u8* in, const u64* in_off, const u64* usz, u8* stage, u64 stride, u64* csz,
-                                  u32 n, u32* ticket, int sm_count, cudaStream_t st, const u64* n_dev, u32* tail_pos, u32* tail_len, const u32* hist)
+                                  u32 n, u32* ticket, int sm_count, cudaStream_t st, const u64* n_dev, u32* tail_pos, u32* tail_len, const u32* hist, u64* prof)
 {
     static bool attr = false;
     if (!attr) {
@@ -416,18 +426,18 @@ inline cudaError_t c2_launch_mode(const u8* in, const u64* in_off, const u64* us
     if (grid > n) grid = n;
     cudaError_t e = cudaMemsetAsync(ticket, 0, sizeof(u32), st);
     if (e != cudaSuccess) return e;
-    compress_c2_kernel<MODE><<<grid, C2_THREADS, C2Smem::BYTES, st>>>(in, in_off, usz, stage, stride, csz, n, ticket, n_dev, tail_pos, tail_len, hist);
+    compress_c2_kernel<MODE><<<grid, C2_THREADS, C2Smem::BYTES, st>>>(in, in_off, usz, stage, stride, csz, n, ticket, n_dev, tail_pos, tail_len, hist, prof);
     return cudaGetLastError();
 }
 
 inline cudaError_t c2_launch_compress(const u8* in, const u64* in_off, const u64* usz, u8* stage, u64 stride, u64* csz,
                                       u32 n, u32* ticket, int sm_count, cudaStream_t st, const u64* n_dev = nullptr,
-                                      u32* tail_pos = nullptr, u32* tail_len = nullptr, const u32* hist = nullptr)
+                                      u32* tail_pos = nullptr, u32* tail_len = nullptr, const u32* hist = nullptr, u64* prof = nullptr)
 {
     switch (c1_mode()) {
-    case 0:  return c2_launch_mode<0>(in, in_off, usz, stage, stride, csz, n, ticket, sm_count, st, n_dev, tail_pos, tail_len, hist);
-    case 2:  return c2_launch_mode<2>(in, in_off, usz, stage, stride, csz, n, ticket, sm_count, st, n_dev, tail_pos, tail_len, hist);
-    default: return c2_launch_mode<1>(in, in_off, usz, stage, stride, csz, n, ticket, sm_count, st, n_dev, tail_pos, tail_len, hist);
+    case 0:  return c2_launch_mode<0>(in, in_off, usz, stage, stride, csz, n, ticket, sm_count, st, n_dev, tail_pos, tail_len, hist, prof);
+    case 2:  return c2_launch_mode<2>(in, in_off, usz, stage, stride, csz, n, ticket, sm_count, st, n_dev, tail_pos, tail_len, hist, prof);
+    default: return c2_launch_mode<1>(in, in_off, usz, stage, stride, csz, n, ticket, sm_count, st, n_dev, tail_pos, tail_len, hist, prof);
     }
 }
 

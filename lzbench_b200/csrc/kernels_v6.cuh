@@ -60,7 +60,7 @@ decompress_v6_kernel(const __grid_constant__ V5Params P)
 
     bool busy = false, exhausted = false, fastable = false;
     u8* dst = nullptr;
-    u32 ip = 0, op = 0, tok = 0, op_safe = 0, ip_safe = 0, rem = 0, roff = 0;
+    u32 ip = 0, op = 0, tok = 0, op_safe = 0, ip_safe = 0, rem = 0, roff = 0, lrem = 0;
     u32 meta[DEPTH];                                 // meta[0]: part fetched DEPTH iterations ago (stored now) ... meta[DEPTH-1]: last iteration's
     #pragma unroll
     for (u32 k = 0; k < DEPTH; k++) meta[k] = 0;
@@ -70,28 +70,36 @@ decompress_v6_kernel(const __grid_constant__ V5Params P)
         cp_async_wait<DEPTH - 1>();                  // the group committed DEPTH iterations ago has landed
         __syncwarp();                                // ... and is visible to every lane of the team
         // ---- A: decode the current token of every team (warp level, no branches); see kernels_v4.cuh / v5 ----
-        const bool cont = rem != 0;
+        const bool cont = rem != 0, lcont = lrem != 0;
         const u32 Lt = tok >> 4, M = tok & ML_MASK;
-        const u32 L = cont ? 0u : Lt;
+        const u32 e1 = ring[(ip + 1) & (RING - 1)];      // literal length byte, if the nibble is 15
+        const bool lext = Lt == RUN_MASK;
+        const u32 LL = lcont ? lrem : (lext ? 15u + e1 : Lt);                    // literals owed before the match
+        const u32 lpos = ip + (lcont ? 0u : (lext ? 2u : 1u));                    // stream position of the next literal
+        const bool lonly = !cont && LL > 16u;                                      // this iteration: 16 literals, nothing else
+        const u32 L = cont ? 0u : (lonly ? 16u : LL);
         const u32 cpy = op + L;
-        const u32 rp = ip + 1;
-        const u32 lo = ring[(rp + Lt) & (RING - 1)];
-        const u32 hi = ring[(rp + Lt + 1) & (RING - 1)];
-        const u32 e = ring[(rp + Lt + 2) & (RING - 1)];
+        const u32 mp = lpos + LL;                        // stream position of the match offset
+        const u32 lo = ring[mp & (RING - 1)];
+        const u32 hi = ring[(mp + 1) & (RING - 1)];
+        const u32 e = ring[(mp + 2) & (RING - 1)];       // match length byte, if the nibble is 15
         const bool ext = M == ML_MASK;
         const u32 off = cont ? roff : (lo | (hi << 8));
         const u32 ml_total = cont ? rem : (ext ? 19u + e : M + MINMATCH);
-        const u32 ml = ml_total < V6_PART ? ml_total : V6_PART;
-        const u32 nip = ip + Lt + 3 + (ext ? 1u : 0u);
-        const bool f = fastable && (cont || (tok < 0xF0u && (!ext || (Lt <= 13u && e != 255u)) &&
-                                            cpy + ml_total <= op_safe && ip + Lt <= ip_safe && off <= cpy)) &&
-                       off >= ml;
+        const u32 ml = lonly ? 0u : (ml_total < V6_PART ? ml_total : V6_PART);
+        const u32 nip = mp + 2 + (ext ? 1u : 0u);
+        const u32 c_cont = cont, c_lcont = lcont, c_lonly = lonly;           // bitwise on purpose, see kernels_v5.cuh
+        const u32 c_hdr = c_cont | c_lcont | ((u32)(!lext | (e1 != 255u)) & (u32)(mp <= ip_safe));
+        const u32 c_lit = (u32)(cpy + 16u <= op_safe);
+        const u32 c_mat = (c_cont | ((u32)(!ext | (e != 255u)) & (u32)(cpy + ml_total <= op_safe) & (u32)(off <= cpy))) &
+                          (u32)(off >= ml);
+        const bool f = ((u32)fastable & c_hdr & (c_lonly ? c_lit : c_mat)) != 0;
         const u32 sbase = cpy - off;
         // pending destinations are contiguous and end at op: the match may read nothing at or after the oldest one
         u32 pend_lo = 0xFFFFFFFFu;
         #pragma unroll
         for (u32 k = DEPTH - 1; k >= 1; k--) if (v6_len(meta[k])) pend_lo = v6_dst(meta[k], op);
-        const bool flush = busy && (!f || sbase + ml > pend_lo);
+        const bool flush = busy && (!f || (ml != 0 && sbase + ml > pend_lo));
 
         // ---- B: store the part fetched DEPTH iterations ago; the younger ones only if somebody has to ----
         v6_store<T>(meta[0], stage + si * V6_SLOT, dst, op, j);
@@ -113,7 +121,7 @@ decompress_v6_kernel(const __grid_constant__ V5Params P)
             const u32 lim = f ? L : 0u;
             #pragma unroll
             for (u32 k = 0; k < NX; k++) {
-                const u32 val = ring[(rp + i0 + k * T) & (RING - 1)];
+                const u32 val = ring[(lpos + i0 + k * T) & (RING - 1)];
                 if (i0 + k * T < lim) p[k * T] = (u8)val;
             }
         }
@@ -123,16 +131,20 @@ decompress_v6_kernel(const __grid_constant__ V5Params P)
         for (u32 k = 0; k + 1 < DEPTH; k++) meta[k] = meta[k + 1];
         meta[DEPTH - 1] = 0;
         if (f) {
-            const u8* q = dst + sbase;
-            const u32 soff = (u32)(reinterpret_cast<uintptr_t>(q) & 15u);
-            if (j == 0 || (j == 1 && soff + ml > 16u)) cp_async16(stage + si * V6_SLOT + j * 16, q - soff + j * 16, 16u);
-            meta[DEPTH - 1] = (ml << 27) | (soff << 23) | (cpy & 0x7FFFFFu);
-            if (!cont) {
-                if (nip / SEG != ip / SEG) v5_request<T>(ring, ts.src, ts.clen, nip / SEG + 2, j);
-                tok = ring[nip & (RING - 1)];
-                ip = nip; roff = off;
+            const u32 ip2 = lonly ? lpos + 16u : nip;
+            if (!lonly) {
+                const u8* q = dst + sbase;
+                const u32 soff = (u32)(reinterpret_cast<uintptr_t>(q) & 15u);
+                if (j == 0 || (j == 1 && soff + ml > 16u)) cp_async16(stage + si * V6_SLOT + j * 16, q - soff + j * 16, 16u);
+                meta[DEPTH - 1] = (ml << 27) | (soff << 23) | (cpy & 0x7FFFFFu);
             }
-            rem = ml_total - ml;
+            if (!cont) {
+                if (ip2 / SEG != ip / SEG) v5_request<T>(ring, ts.src, ts.clen, ip2 / SEG + 2, j);
+                if (lonly) lrem = LL - 16u;
+                else { tok = ring[nip & (RING - 1)]; roff = off; lrem = 0; }
+                ip = ip2;
+            }
+            if (!lonly) rem = ml_total - ml;
             op = cpy + ml;
         }
         cp_async_commit();
@@ -140,13 +152,13 @@ decompress_v6_kernel(const __grid_constant__ V5Params P)
 
         // ---- everything else, behind one vote and one call (slow teams have nothing pending: all flushed) ----
         if (!__any_sync(FULL, (busy && !f) || (!busy && !exhausted))) continue;
-        V5State S{ dst, ip, op, tok, 0u, op_safe, ip_safe, rem, busy, exhausted, fastable };
+        V5State S{ dst, ip, op, tok, 0u, op_safe, ip_safe, rem, busy, exhausted, fastable, lrem };
         const bool done = v5_cold<T>(S, f, P, ring, ts);
         dst = S.dst; ip = S.ip; op = S.op; tok = S.tok; op_safe = S.op_safe; ip_safe = S.ip_safe;
-        rem = S.rem; busy = S.busy; exhausted = S.exhausted; fastable = S.fastable;
+        rem = S.rem; busy = S.busy; exhausted = S.exhausted; fastable = S.fastable; lrem = S.lrem;
         if (done) break;
         {   // consume the restored values on this side of the back edge (see kernels_v5.cuh: scoreboard sharing)
-            const u32 sink = ip ^ op ^ tok ^ op_safe ^ ip_safe ^ rem ^ (u32)reinterpret_cast<uintptr_t>(dst) ^
+            const u32 sink = ip ^ op ^ tok ^ op_safe ^ ip_safe ^ rem ^ lrem ^ (u32)reinterpret_cast<uintptr_t>(dst) ^
                              (u32)(reinterpret_cast<uintptr_t>(dst) >> 32) ^ (u32)busy ^ (u32)exhausted ^ (u32)fastable;
             if (sink == 0x9E3779B9u) v6_sink = sink;
         }

@@ -246,7 +246,8 @@ int compress_slice(lz4b200_ctx* c, const u8* d_in, const u64* d_usz, size_t n, s
         seg_stitch_size_kernel<<<gb, 256, 0, st>>>(sa, s.stage, slot_stride_for(SEG_BYTES), d_csz, (u32)n);
         c->launches += 5;
     } else if (c->compress_gen == 2 && c1_compress_supported(max_chunk)) {
-        CU(c2_launch_compress(d_in, s.uoff, d_usz, s.stage, stride, d_csz, (u32)n, s.ticket, c->sm_count, st));
+        CU(c2_launch_compress(d_in, s.uoff, d_usz, s.stage, stride, d_csz, (u32)n, s.ticket, c->sm_count, st, nullptr, nullptr, nullptr,
+                              nullptr, c->prof_on ? (u64*)c->prof.p : nullptr));
         c->launches++;
     } else if (c->compress_gen == 1 && c1_compress_supported(max_chunk)) {
         CU(c1_launch_compress(d_in, s.uoff, d_usz, s.stage, stride, d_csz, (u32)n, s.ticket,

@@ -74,7 +74,12 @@ for kind in kinds:
             tot = sum(pr[:8]) or 1
             print("   decode phases [ticket,load,parse,scan,literals,matches,(coop),store] %:",
                   [round(100 * x / tot, 1) for x in pr[:7]], "cycles/chunk", tot // n_chunks, flush=True)
-        if gen != "v0" and os.environ.get("PROF"):
+        if gen in ("c2", "v5t8") and os.environ.get("PROF"):
+            ctx.set_option("prof", "1"); comp(); pr = ctx.debug_prof(); ctx.set_option("prof", "0")
+            tiles = n_chunks * 16
+            print("   c2 cycles/tile: A match %d, A wait-empty %d | B wait-full %d, B parse %d, B emit %d | stage/chunk %d | rounds/tile %.2f"
+                  % (pr[0] // tiles, pr[1] // tiles, pr[2] // tiles, pr[3] // tiles, pr[4] // tiles, pr[5] // n_chunks, pr[7] / tiles), flush=True)
+        elif gen != "v0" and os.environ.get("PROF"):
             ctx.set_option("prof", "1"); comp(); pr = ctx.debug_prof(); ctx.set_option("prof", "0")
             tot = sum(pr[8:13]) or 1
             print("   compress phases [load,match,parse,emit,final] %:", [round(100 * x / tot, 1) for x in pr[8:13]],
