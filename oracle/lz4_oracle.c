@@ -66,6 +66,15 @@ static inline uint32_t count_eq(const uint8_t* src, uint32_t a, uint32_t b, uint
  * outputDirective in {notLimited, limitedOutput} picked as in :1290-1303. */
 int oracle_lz4_compress(const uint8_t* src, int n, uint8_t* dst, int cap)
 {
+    return oracle_lz4_compress_fast(src, n, dst, cap, 1);
+}
+
+/* LZ4_compress_fast (lz4/lz4.c:1352-1375: acceleration < 1 -> 1, > 65537 -> 65537; the `lz4fast` rows of lzbench,
+ * _lzbench/compressors.cpp:348-356): the skip counter of the search loop starts at acceleration << 6 (:985). */
+int oracle_lz4_compress_fast(const uint8_t* src, int n, uint8_t* dst, int cap, int acceleration)
+{
+    if (acceleration < 1) acceleration = 1;
+    if (acceleration > 65537) acceleration = 65537;
     uint32_t table[1 << HASHLOG_U32];            /* 16 KB, doubles as u16[8192] logically */
     if (n < 0 || (unsigned)n > (unsigned)MAX_INPUT) return 0;
     const int limited = cap < oracle_lz4_compress_bound(n);
@@ -89,7 +98,7 @@ int oracle_lz4_compress(const uint8_t* src, int n, uint8_t* dst, int cap)
     for (;;) {
         uint32_t match, tok_pos;
         {   /* :983-1014 search loop with skip acceleration */
-            uint32_t fwd_ip = ip, step = 1, nb = 1u << SKIP_TRIGGER;
+            uint32_t fwd_ip = ip, step = 1, nb = (uint32_t)acceleration << SKIP_TRIGGER;
             for (;;) {
                 uint32_t h = fwd_h, cur = fwd_ip;
                 uint32_t cand = TGET(h);

@@ -30,6 +30,8 @@ int oracle_lz4_compress_bound(int n);
 /* lz4/lz4.c:1373 LZ4_compress_default -> :1354 -> :1284 -> :851 (acceleration = 1).
  * Returns bytes written, 0 if dst too small (limitedOutput path). */
 int oracle_lz4_compress(const uint8_t* src, int n, uint8_t* dst, int cap);
+/* LZ4_compress_fast, lz4/lz4.c:1352-1375 */
+int oracle_lz4_compress_fast(const uint8_t* src, int n, uint8_t* dst, int cap, int acceleration);
 
 /* lz4/lz4.c:2171 LZ4_decompress_safe semantics (endOnInputSize, full block, noDict).
  * Returns bytes written or a negative value on malformed input. */

@@ -22,6 +22,7 @@ orc = C.CDLL(ORACLE_SO)
 orc.oracle_lz4_compress_bound.argtypes = [C.c_int]
 orc.oracle_lz4_compress.argtypes = [vp, C.c_int, vp, C.c_int]
 orc.oracle_lz4_decompress_safe.argtypes = [vp, C.c_int, vp, C.c_int]
+orc.oracle_lz4_compress_fast.argtypes = [vp, C.c_int, vp, C.c_int, C.c_int]
 orc.oracle_lz4_validate.argtypes = [vp, C.c_int, C.c_int, C.POINTER(SeqStats)]
 orc.oracle_lzbench_compress.restype = C.c_int64
 orc.oracle_lzbench_compress.argtypes = [vp, vp, C.c_size_t, vp, vp, vp, C.c_size_t]
@@ -37,6 +38,7 @@ if os.path.exists(REF_SO):
     ref = C.CDLL(REF_SO)
     ref.LZ4_compress_default.argtypes = [vp, vp, C.c_int, C.c_int]
     ref.LZ4_decompress_safe.argtypes = [vp, vp, C.c_int, C.c_int]
+    ref.LZ4_compress_fast.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int]
     ref.LZ4_decompress_fast.argtypes = [vp, vp, C.c_int]
     ref.LZ4_compressBound.argtypes = [C.c_int]
     ref.LZ4_versionString.restype = C.c_char_p

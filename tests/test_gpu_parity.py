@@ -255,3 +255,35 @@ def test_device_resident_roundtrip_5g_64bit_offsets(gpu_ctx):
         plain = d_in[i * chunk:(i + 1) * chunk].cpu().numpy()
         r, out = O.oracle_decompress(blk, chunk)
         assert r == chunk and np.array_equal(out, plain)
+
+
+def test_many_small_files_mode(gpu_ctx):
+    """lzbench -j joins many small files and cuts every FILE into chunks, so the chunk list is
+    ragged (_lzbench/lzbench.cpp:366-373, :537-620): thousands of files from 1 byte up, chunked at 4 KiB and 64 KiB."""
+    rng = np.random.default_rng(11)
+    files = np.concatenate([rng.integers(1, 40, 2000), rng.integers(40, 5000, 6000), rng.integers(5000, 300000, 150)])
+    rng.shuffle(files)
+    n = int(files.sum())
+    data = L.corpus("mixed", n, seed=6)
+    for chunk in (4096, 65536):
+        cs = L.chunk_list(files, chunk)
+        assert int(cs.sum()) == n and int(cs.max()) <= chunk and len(cs) >= len(files)
+        packed, compr, total = gpu_ctx.compress_batch(data, cs)
+        out, r = gpu_ctx.decompress_batch(packed[:total], compr, cs)
+        assert r == n and np.array_equal(out, data)
+        p2, c2 = O.oracle_chunked_compress(data, cs)
+        assert total <= RATIO_TOLERANCE * len(p2)
+        out, r = gpu_ctx.decompress_batch(p2, c2, cs)
+        assert r == n and np.array_equal(out, data)
+        # spot-check blocks with the reference decoder (every 37th chunk)
+        off_p = np.concatenate([[0], np.cumsum(compr)]).astype(np.int64)
+        off_u = np.concatenate([[0], np.cumsum(cs)]).astype(np.int64)
+        for i in range(0, len(cs), 37):
+            z, u = int(compr[i]), int(cs[i])
+            blk, plain = packed[off_p[i]:off_p[i] + z], data[off_u[i]:off_u[i] + u]
+            if z == u:
+                assert np.array_equal(blk, plain)
+            else:
+                rr, o = O.oracle_decompress(blk, u)
+                assert rr == u and np.array_equal(o, plain)
+

@@ -145,3 +145,17 @@ def test_mt_driver_matches_serial():
     ns = O.orc.oracle_mt_run(O.PLUGIN_DECOMPRESS, 1, 3, cs.ctypes.data, compr.ctypes.data, len(cs),
                              out.ctypes.data, packed.ctypes.data, stride)
     assert ns > 0 and np.array_equal(out, data)
+
+
+@needs_ref
+@pytest.mark.parametrize("accel", [0, 1, 2, 4, 8, 17, 64, 99])
+def test_oracle_compress_fast_is_byte_identical_to_reference(accel):
+    """the `lz4fast` levels (LZ4_compress_fast, _lzbench/compressors.cpp:348-356)."""
+    for name, data in corpora(1 << 18):
+        for chunk in (4096, 65536, 1 << 18):
+            part = data[:chunk]
+            cap = O.orc.oracle_lz4_compress_bound(len(part))
+            a = np.zeros(cap, dtype=np.uint8); b = np.zeros(cap, dtype=np.uint8)
+            ra = O.orc.oracle_lz4_compress_fast(part.ctypes.data, len(part), a.ctypes.data, cap, accel)
+            rb = O.ref.LZ4_compress_fast(part.ctypes.data, b.ctypes.data, len(part), cap, accel)
+            assert ra == rb and np.array_equal(a[:ra], b[:rb]), (name, chunk, accel)
