@@ -333,6 +333,8 @@ def run_b200(args):
     # ---- compress ----
     c_ms, c_kt, c_launches, c_win = timed(compress_dev, K, W)
     e2e_c = timed_host(lambda: ctx.compress_batch(h_plain, h_cs, h_out), max(2, K // 2), W)
+    # yardstick: the same U bytes host -> device -> host through the same staging, no kernel (the reference's cudaMemcpy row)
+    e2e_m = timed_host(lambda: ctx.memcpy_batch(h_plain, U, h_back), max(2, K // 2), W)
 
     clocks = None
     if sampler is not None:
@@ -379,7 +381,9 @@ def run_b200(args):
         "roofline": roof(d_kt, "decompress"),
         "e2e": {"value": world * U / e2e_d / GB, "unit": "GB/s", "h2d_bytes_per_step": int(Cb + 16 * n_chunks),
                 "d2h_bytes_per_step": int(U + 4), "ms_per_step": e2e_d * 1e3,
-                "api": "lz4b200_decompress_batch (pinned host buffers)"},
+                "api": "lz4b200_decompress_batch (pinned host buffers)",
+                "pcie_yardstick": {"value": world * U / e2e_m / GB, "unit": "GB/s", "ms_per_step": e2e_m * 1e3,
+                                   "what": "lz4b200_memcpy_batch: the same U bytes host->device->host, no kernel"}},
         "gpu_launches": int(d_launches),
         "clocks": clocks,
         "compress": {"value": world * U / (c_ms * 1e-3) / GB, "unit": "GB/s", "ms_per_step": c_ms,

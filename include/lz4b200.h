@@ -133,6 +133,11 @@ int64_t lzbench_lz4_b200_compress_batch(const size_t* chunk_sizes, size_t n_chun
 int64_t lzbench_lz4_b200_decompress_batch(const size_t* chunk_sizes, const size_t* compr_sizes, size_t n_chunks,
                                           char* in, char* out, char* workmem);
 
+/* ---- PCIe yardstick -------------------------------------------------
+ * What the reference's `cudaMemcpy` row does (lzbench_cuda_memcpy, _lzbench/compressors.cpp:1826-1831): n bytes host ->
+ * device -> host, no kernel, through this library's staging (page-locked buffers, overlapped slices).  Returns n. */
+int64_t lz4b200_memcpy_batch(lz4b200_ctx* ctx, const char* in, size_t n, char* out);
+
 /* ---- LZ4 frame container around the chunked path -------------------
  * A frame with independent blocks is the chunked hot path plus framing: magic, descriptor, one LE32 size word per
  * block (bit 31 = stored uncompressed), end mark, optional xxHash32 checksums (lz4/lz4frame.h:119-186 for the types

@@ -67,6 +67,8 @@ def _load() -> C.CDLL:
     L.lzbench_lz4_b200_compress_batch.argtypes = [vp, sz, vp, vp, vp, sz, vp]
     L.lzbench_lz4_b200_decompress_batch.restype = i64
     L.lzbench_lz4_b200_decompress_batch.argtypes = [vp, vp, sz, vp, vp, vp]
+    L.lz4b200_memcpy_batch.restype = i64
+    L.lz4b200_memcpy_batch.argtypes = [vp, vp, sz, vp]
     L.lz4b200_frame_bound.restype = sz
     L.lz4b200_frame_bound.argtypes = [sz, C.c_int]
     L.lz4b200_frame_compress.restype = i64
@@ -210,6 +212,10 @@ class Lz4B200:
             outbuf = np.zeros(int(cs.sum()), dtype=np.uint8)
         r = lib.lz4b200_decompress_batch(self._h, _ptr(inbuf), zs.ctypes.data, cs.ctypes.data, len(cs), _ptr(outbuf))
         return outbuf, int(r)
+
+    def memcpy_batch(self, inbuf, n: int, outbuf) -> int:
+        """PCIe yardstick: n bytes host -> device -> host, no kernel (the reference's cudaMemcpy row)."""
+        return int(lib.lz4b200_memcpy_batch(self._h, _ptr(inbuf), n, _ptr(outbuf)))
 
     # -- LZ4 frame container (lz4/lz4frame.h LZ4F_compressFrame / LZ4F_decompress; independent blocks) ------
     def frame_compress(self, data, block_id: int = 4, content_checksum: bool = False, block_checksum: bool = False,

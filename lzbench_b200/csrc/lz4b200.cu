@@ -744,6 +744,32 @@ int64_t lz4b200_decompress_batch(lz4b200_ctx* c, const char* in, const size_t* c
     return (int64_t)total;
 }
 
+// The yardstick for e2e: what the reference's `cudaMemcpy` row measures (lzbench_cuda_memcpy,
+// _lzbench/compressors.cpp:1826-1831: H2D then D2H of the same bytes), through this library's plumbing -- page-locked
+// caller buffers, slices on the pipeline streams so the two directions overlap.  No kernel runs.
+int64_t lz4b200_memcpy_batch(lz4b200_ctx* c, const char* in, size_t n, char* out)
+{
+    if (!c) return fail(-1, "null ctx");
+    if (n == 0) return 0;
+    if (!in || !out) return fail(-1, "null argument");
+    CU(cudaSetDevice(c->device));
+    maybe_register(c, in, n);
+    maybe_register(c, out, n);
+    CU(c->d_plain.ensure(n + 16));
+    const int K = n >= (512u << 20) ? 16 : (n >= (32u << 20) ? 4 : 1);
+    if (int rc = ensure_events(c, K)) return rc;
+    for (int k = 0; k < K; k++) {
+        const size_t lo = n * k / K, hi = n * (k + 1) / K;
+        cudaStream_t st = c->streams[k % lz4b200_ctx::NS];
+        CU(cudaMemcpyAsync((u8*)c->d_plain.p + lo, in + lo, hi - lo, cudaMemcpyHostToDevice, st));
+        CU(cudaEventRecord(c->ev_done[k], st));
+        CU(cudaStreamWaitEvent(c->d2h_stream, c->ev_done[k], 0));
+        CU(cudaMemcpyAsync(out + lo, (u8*)c->d_plain.p + lo, hi - lo, cudaMemcpyDeviceToHost, c->d2h_stream));
+    }
+    CU(cudaStreamSynchronize(c->d2h_stream));
+    return (int64_t)n;
+}
+
 // ---- LZ4 frame container (frame.cuh) -----------------------------------------------------------
 
 size_t lz4b200_frame_bound(size_t n, int block_id)
