@@ -334,7 +334,7 @@ def run_b200(args):
     c_ms, c_kt, c_launches, c_win = timed(compress_dev, K, W)
     e2e_c = timed_host(lambda: ctx.compress_batch(h_plain, h_cs, h_out), max(2, K // 2), W)
     # yardstick: the same U bytes host -> device -> host through the same staging, no kernel (the reference's cudaMemcpy row)
-    e2e_m = timed_host(lambda: ctx.memcpy_batch(h_plain, U, h_back), max(2, K // 2), W)
+    e2e_m = timed_host(lambda: ctx.memcpy_batch(h_plain, n, h_back), max(2, K // 2), W)
 
     clocks = None
     if sampler is not None:
