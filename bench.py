@@ -354,7 +354,7 @@ def run_b200(args):
     # dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full captures under profiles/
     # (profiles/README.md), valid for the default workload only (1 GiB mixed, 64 KiB chunks, default kernels)
     default_cfg = args.size_mib == 1024 and chunk == 65536 and args.corpus == "mixed" and not args.kernels
-    traffic = {"decompress": 3.5466e9 if default_cfg else None,          # profiles/r01_final_decompress_v4_ncu_raw.csv
+    traffic = {"decompress": 3.4254e9 if default_cfg else None,          # profiles/r01_final_decompress_v5_ncu_raw.csv
                "compress": 1.6951e9 if default_cfg else None}            # profiles/r01_final_compress_c2_ncu_raw.csv
 
     def roof(kt, which):
