@@ -213,7 +213,7 @@ def run_reference(args):
         "e2e": {"value": dec, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "wall_s": wall,
     }
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 def run_b200(args):
@@ -409,13 +409,33 @@ def run_b200(args):
         line["cpu_baseline"]["lzbench_row"] = lzbench_row(h_plain.numpy()[:min(sample, 256 << 20)], chunk)
         line["compress"]["ratio_pct"] = 100.0 * Cb / U
         line["compress"]["size_vs_reference"] = gpu_sample_bytes / cb["compressed_bytes"]
-    print(json.dumps(line), flush=True)
+    _emit(line)
     if dist is not None:
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def _quiet_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries print there too (NCCL's version banner under torchrun), so
+    file descriptor 1 points at stderr until the line is ready."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
+def _emit(line):
+    sys.stdout.flush()
+    if _REAL_STDOUT is not None:
+        os.dup2(_REAL_STDOUT, 1)
+    print(json.dumps(line), flush=True)
+
+
 def main():
     args = parse_args()
+    _quiet_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:
