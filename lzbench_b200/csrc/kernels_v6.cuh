@@ -26,20 +26,42 @@ constexpr u32 V6_SLOT = 32;                          // staging bytes per pendin
 __device__ __forceinline__ u32 v6_len(u32 meta) { return meta >> 27; }
 __device__ __forceinline__ u32 v6_dst(u32 meta, u32 op) { return op - ((op - meta) & 0x7FFFFFu); }
 
-// store a landed slot: lane j writes the output positions == j (mod T)
+// A landed slot goes out in two steps so that the shared-memory reads of everything an iteration stores (the slot and
+// the literals) are issued together, ahead of the first store that needs them: with 3-7 warps per scheduler an LDS
+// directly in front of its ST is a 30-cycle stall each time (short scoreboard: 60 % of the stall samples of the first
+// version).  Lane j owns the output positions == j (mod T).
+template <u32 T>
+struct V6Out { u32 val[(V6_PART + T - 1) / T]; u32 len, i0; u8* p; };
+
+template <u32 T>
+__device__ __forceinline__ void v6_load(V6Out<T>& o, u32 meta, const u8* slot, u8* dst, u32 op, u32 j)
+{
+    constexpr u32 NM = (V6_PART + T - 1) / T;
+    const u32 sdst = v6_dst(meta, op), soff = (meta >> 23) & 15u;
+    o.len = v6_len(meta);
+    o.i0 = (j - sdst) & (T - 1);
+    o.p = dst + (sdst + o.i0);
+    #pragma unroll
+    for (u32 k = 0; k < NM; k++) o.val[k] = slot[soff + o.i0 + k * T];
+}
+
+template <u32 T>
+__device__ __forceinline__ void v6_put(const V6Out<T>& o)
+{
+    constexpr u32 NM = (V6_PART + T - 1) / T;
+    u8* p = o.p;
+    asm volatile("" : "+l"(p));                      // one address computation for the predicated stores below
+    #pragma unroll
+    for (u32 k = 0; k < NM; k++)
+        if (o.i0 + k * T < o.len) p[k * T] = (u8)o.val[k];
+}
+
 template <u32 T>
 __device__ __forceinline__ void v6_store(u32 meta, const u8* slot, u8* dst, u32 op, u32 j)
 {
-    constexpr u32 NM = (V6_PART + T - 1) / T;
-    const u32 len = v6_len(meta), sdst = v6_dst(meta, op), soff = (meta >> 23) & 15u;
-    const u32 i0 = (j - sdst) & (T - 1);
-    u8* p = dst + (sdst + i0);
-    asm volatile("" : "+l"(p));                      // one address computation for the predicated stores below
-    #pragma unroll
-    for (u32 k = 0; k < NM; k++) {
-        const u32 val = slot[soff + i0 + k * T];
-        if (i0 + k * T < len) p[k * T] = (u8)val;
-    }
+    V6Out<T> o;
+    v6_load<T>(o, meta, slot, dst, op, j);
+    v6_put<T>(o);
 }
 
 template <u32 T, u32 DEPTH>
@@ -101,8 +123,15 @@ decompress_v6_kernel(const __grid_constant__ V5Params P)
         for (u32 k = DEPTH - 1; k >= 1; k--) if (v6_len(meta[k])) pend_lo = v6_dst(meta[k], op);
         const bool flush = busy && (!f || (ml != 0 && sbase + ml > pend_lo));
 
-        // ---- B: store the part fetched DEPTH iterations ago; the younger ones only if somebody has to ----
-        v6_store<T>(meta[0], stage + si * V6_SLOT, dst, op, j);
+        // ---- B + C: the part fetched DEPTH iterations ago and this sequence's literals: all reads, then all stores;
+        //      the younger parts only if somebody has to ----
+        V6Out<T> ob;
+        v6_load<T>(ob, meta[0], stage + si * V6_SLOT, dst, op, j);
+        u32 lit[NX];
+        const u32 li0 = (j - op) & (T - 1);
+        #pragma unroll
+        for (u32 k = 0; k < NX; k++) lit[k] = ring[(lpos + li0 + k * T) & (RING - 1)];
+        v6_put<T>(ob);
         if (__any_sync(FULL, flush)) {
             cp_async_wait<0>();
             __syncwarp();
@@ -113,17 +142,13 @@ decompress_v6_kernel(const __grid_constant__ V5Params P)
                 meta[k] = 0;
             }
         }
-        // ---- C: literal run, straight from the ring ----
         {
-            const u32 i0 = (j - op) & (T - 1);
-            u8* p = dst + (op + i0);
+            u8* p = dst + (op + li0);
             asm volatile("" : "+l"(p));
             const u32 lim = f ? L : 0u;
             #pragma unroll
-            for (u32 k = 0; k < NX; k++) {
-                const u32 val = ring[(lpos + i0 + k * T) & (RING - 1)];
-                if (i0 + k * T < lim) p[k * T] = (u8)val;
-            }
+            for (u32 k = 0; k < NX; k++)
+                if (li0 + k * T < lim) p[k * T] = (u8)lit[k];
         }
         __syncwarp();                                // stores of B and C (all lanes) -> visible to the fetches below
         // ---- D: fetch this part's source blocks into the slot just emptied, and the next ring segment if due ----
