@@ -315,7 +315,11 @@ int decompress_slice(lz4b200_ctx* c, const u8* d_in, const u64* d_csz, const u64
     // on wider teams, and wider teams also spread few chunks over more SMs
     if (!team) team = c->team;
     if (!team) {
-        if (c->kernel_gen >= 5) team = n * 2 <= (size_t)c->sm_count * 32 ? 16 : 8;      // measured (scripts/team_probe.py): 1024 chunks take 2.0 ms on 16 lanes, 2.6 on 8, 3.7 on a warp (v2)
+        // measured (scripts/team_probe.py, gpu_probe.py): 1024 chunks take 2.0 ms on 16 lanes, 2.6 on 8, 3.7 on a warp (v2);
+        // 4-lane teams (8 chunks per warp) only pay once there are enough chunks to fill the machine with them
+        // (262 144 chunks of 4 KiB: 357 vs 301 GB/s; 65 536 of 16 KiB: 250 vs 294)
+        if (c->kernel_gen == 5) team = n * 2 <= (size_t)c->sm_count * 32 ? 16 : (n >= (size_t)c->sm_count * 7 * 32 * 4 ? 4 : 8);
+        else if (c->kernel_gen >= 5) team = n * 2 <= (size_t)c->sm_count * 32 ? 16 : 8;
         else team = n * 4 <= (size_t)c->sm_count * 32 ? 32 : (n * 2 <= (size_t)c->sm_count * 32 ? 16 : 8);
     }
     if (c->kernel_gen == 6 && team != 32) {
