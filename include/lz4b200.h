@@ -150,11 +150,11 @@ int64_t lz4b200_memcpy_batch(lz4b200_ctx* ctx, const char* in, size_t n, char* o
 /* Upper bound of a frame holding n bytes in blocks of id block_id (4..7 = 64 KiB, 256 KiB, 1 MiB, 4 MiB;
  * LZ4F_blockSizeID_t, lz4/lz4frame.h:123-133).  Replaces LZ4F_compressFrameBound, lz4/lz4frame.h:215.  0 = bad id. */
 size_t  lz4b200_frame_bound(size_t n, int block_id);
-/* Replaces LZ4F_compressFrame (lz4/lz4frame.h:224, lz4/lz4frame.c:398-470) with blockMode = LZ4F_blockIndependent.
+/* Replaces LZ4F_compressFrame (lz4/lz4frame.h:224, lz4/lz4frame.c:429-470) with blockMode = LZ4F_blockIndependent.
  * Host buffers.  Returns the frame size, or < 0. */
 int64_t lz4b200_frame_compress(lz4b200_ctx* ctx, const char* in, size_t n, char* out, size_t out_capacity,
                                int block_id, int flags);
-/* Replaces one complete LZ4F_decompress session (lz4/lz4frame.h:465, lz4/lz4frame.c:1372-1750) over one frame.
+/* Replaces one complete LZ4F_decompress session (lz4/lz4frame.h:465, lz4/lz4frame.c:1384-1830) over one frame.
  * Returns the decoded size; -1 malformed / checksum mismatch / does not fit, -2 valid but outside the chunked path. */
 int64_t lz4b200_frame_decompress(lz4b200_ctx* ctx, const char* in, size_t in_size, char* out, size_t out_capacity,
                                  int flags);

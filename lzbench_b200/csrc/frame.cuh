@@ -1,9 +1,10 @@
 // frame.cuh -- LZ4 frame container around the chunked codec.
-// What the reference implements in lz4/lz4frame.c: LZ4F_compressFrame (:398-470: header, one LE32-prefixed block per
-// blockSize bytes via LZ4F_makeBlock :740-763, end mark, optional content checksum) and LZ4F_decompress (:1372-1750).
+// What the reference implements in lz4/lz4frame.c: LZ4F_compressFrame (lz4/lz4frame.c:429-470: header, one LE32-prefixed
+// block per blockSize bytes via LZ4F_makeBlock lz4/lz4frame.c:740-763, end mark, optional content checksum) and
+// LZ4F_decompress (lz4/lz4frame.c:1384-1830).
 // Here a frame with independent blocks IS the chunked hot path plus a few bytes of framing, so the block work stays
 // on the GPU: sizes -> scan -> header words -> the existing compaction, and for decoding a size pass (a frame does
-// not store decoded block sizes) -> scan -> the existing decoders.  xxHash32 (lz4/xxhash.c) is written from its
+// not store decoded block sizes) -> scan -> the existing decoders.  xxHash32 (lz4/xxhash.c:352-389) is written from its
 // published definition: per block on the device (blocks are independent), whole-content on the host (one serial chain).
 #pragma once
 #include "common.cuh"
@@ -24,7 +25,7 @@ __host__ __device__ inline u32 x_final(u32 h)
 
 // ---- compress side -------------------------------------------------------------------------------------------
 // Block i occupies 4 + csz[i] (+4 with block checksums) bytes in the frame.  A block that did not shrink is stored
-// uncompressed (lz4frame.c:747-752: the block compressor is given srcSize-1 bytes and a failure means "store");
+// uncompressed (lz4/lz4frame.c:747-756: the block compressor is given srcSize-1 bytes and a failure means "store");
 // clamping csz to usz makes the compaction kernels take the raw branch they already have for lzbench's rule.
 __global__ void frame_sizes_kernel(u64* __restrict__ csz, const u64* __restrict__ usz, u64* __restrict__ fsz, u32 n, u32 extra)
 {
@@ -51,7 +52,8 @@ __global__ void frame_headers_kernel(u8* __restrict__ out, u64* __restrict__ off
 
 // xxHash32 (seed 0) of every block payload, one thread per block: the four accumulators are one thread's registers
 // and the 16-byte stripes stream through unaligned word loads.  verify = 0: store the digest behind the payload
-// (LZ4F_makeBlock :758-762); verify = 1: compare with the stored one and count mismatches (LZ4F_decompress :1560-1575).
+// (LZ4F_makeBlock, lz4/lz4frame.c:757-761); verify = 1: compare with the stored one and count mismatches (LZ4F_decompress,
+// lz4/lz4frame.c:1590-1601).
 __global__ void frame_block_xxh_kernel(u8* __restrict__ buf, const u64* __restrict__ off, const u64* __restrict__ len,
                                        u32 n, int verify, u32* __restrict__ bad)
 {
@@ -91,7 +93,7 @@ __global__ void frame_block_xxh_kernel(u8* __restrict__ buf, const u64* __restri
 // the walk leaves it.  hdr[i] = block header word (bit 31 = stored uncompressed).  usz[i] = decoded size, clamped to
 // block_max (the decoder then reports the block as malformed); csz[i] = payload size.  A compressed block that is
 // not smaller than its content cannot be told from a stored one by the decoders' size rule and is counted in
-// *unsupported (the reference encoder never emits one: lz4frame.c:747).
+// *unsupported (the reference encoder never emits one: lz4/lz4frame.c:747).
 constexpr int FS_WARPS = 8;
 constexpr u32 FS_WIN = 1024;
 
@@ -192,7 +194,7 @@ struct FrameInfo {
     u64 content_size = 0;
 };
 
-// lz4frame.c:598-680 (writer) -- version 01, independent blocks, no dictionary
+// lz4/lz4frame.c:598-700 (LZ4F_compressBegin_usingCDict, header bytes :668-700) -- version 01, independent blocks, no dictionary
 inline size_t frame_write_header(u8* dst, int block_id, bool bck, bool cck, bool with_size, u64 content_size)
 {
     h_wr32(dst, F_MAGIC);
@@ -204,7 +206,7 @@ inline size_t frame_write_header(u8* dst, int block_id, bool bck, bool cck, bool
     return (size_t)(p + 1 - dst);
 }
 
-// lz4frame.c:1206-1290 (LZ4F_decodeHeader).  Returns 0, or a negative code with *why set.
+// lz4/lz4frame.c:1113-1204 (LZ4F_decodeHeader).  Returns 0, or a negative code with *why set.
 inline int frame_read_header(const u8* src, size_t n, FrameInfo* fi, const char** why)
 {
     if (n < 7) { *why = "frame shorter than its header"; return -1; }

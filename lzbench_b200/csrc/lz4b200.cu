@@ -784,7 +784,7 @@ size_t lz4b200_frame_bound(size_t n, int block_id)
 }
 
 // One frame, independent blocks of frame_block_bytes(block_id): what LZ4F_compressFrame produces with
-// blockMode = LZ4F_blockIndependent (lz4/lz4frame.c:398-470), except that every block is compressed with a fresh
+// blockMode = LZ4F_blockIndependent (lz4/lz4frame.c:429-470), except that every block is compressed with a fresh
 // table (as lzbench's chunks are) and the block size id is used as given.
 int64_t lz4b200_frame_compress(lz4b200_ctx* c, const char* in, size_t n, char* out, size_t out_capacity,
                                int block_id, int flags)
@@ -811,7 +811,7 @@ int64_t lz4b200_frame_compress(lz4b200_ctx* c, const char* in, size_t n, char* o
         if (end <= 0) return end ? end : fail(-1, "frame exceeds output capacity %zu", out_capacity);
     }
     memcpy(out, hdr, hl);
-    h_wr32((u8*)out + end, 0);                             // end mark, lz4frame.c:917
+    h_wr32((u8*)out + end, 0);                             // end mark, lz4/lz4frame.c:1000-1003
     end += 4;
     if (cck) { h_wr32((u8*)out + end, xxh32_host(in, n)); end += 4; }
     return end;
@@ -825,7 +825,7 @@ int64_t lz4b200_frame_content_size(const char* in, size_t in_size)
     return fi.has_content_size ? (int64_t)fi.content_size : -3;
 }
 
-// LZ4F_decompress for a whole frame with independent blocks (lz4/lz4frame.c:1372-1750).  The host walks the block
+// LZ4F_decompress for a whole frame with independent blocks (lz4/lz4frame.c:1384-1830).  The host walks the block
 // size words (one 4-byte read per block); everything that touches block payloads runs on the device: checksum of
 // every block, a size pass (the frame does not store decoded sizes), and the chunk decoders.
 int64_t lz4b200_frame_decompress(lz4b200_ctx* c, const char* in, size_t in_size, char* out, size_t out_capacity, int flags)

@@ -2,9 +2,11 @@
  * oracle/lz4f_oracle.c -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
  *
  * CPU restatement of the LZ4 frame container as the reference implements it (lz4/lz4frame.c):
- * header (:278-286 constants, LZ4F_compressBegin_usingCDict :598-680), blocks with LE32 size + "uncompressed" bit
- * (LZ4F_makeBlock :740-763), end mark and optional content checksum (LZ4F_compressEnd :905-935), decoder states
- * (LZ4F_decodeHeader :1206-1290, LZ4F_decompress :1372-1750), and xxHash32 (lz4/xxhash.c) for the header byte and
+ * constants lz4/lz4frame.c:210-211, header checksum lz4/lz4frame.c:294-298, header written by
+ * LZ4F_compressBegin_usingCDict lz4/lz4frame.c:598-700, blocks with LE32 size + "uncompressed" bit by LZ4F_makeBlock
+ * lz4/lz4frame.c:740-763, end mark and optional content checksum by LZ4F_compressEnd lz4/lz4frame.c:986-1025, decoder
+ * LZ4F_decodeHeader lz4/lz4frame.c:1113-1204 and LZ4F_decompress lz4/lz4frame.c:1384-1830, and xxHash32
+ * (XXH32_endian_align, lz4/xxhash.c:352-389) for the header byte and
  * the checksums.  Independent blocks only, as in lzbench's chunked mode.  Pinned against oracle/_ref/liblz4fref.so
  * (the reference's lz4frame.c compiled here) by tests/test_frame.py: both directions cross-decode, header bytes equal.
  */
@@ -17,7 +19,7 @@ static inline uint32_t rotl32(uint32_t x, int r) { return (x << r) | (x >> (32 -
 static inline uint32_t rd32le(const uint8_t* p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24); }
 static inline void wr32le(uint8_t* p, uint32_t v) { p[0] = (uint8_t)v; p[1] = (uint8_t)(v >> 8); p[2] = (uint8_t)(v >> 16); p[3] = (uint8_t)(v >> 24); }
 
-/* xxHash32, lz4/xxhash.c XXH32_endian_align */
+/* xxHash32, XXH32_endian_align lz4/xxhash.c:352-389 */
 uint32_t oracle_xxh32(const void* data, size_t len, uint32_t seed)
 {
     const uint32_t P1 = 2654435761U, P2 = 2246822519U, P3 = 3266489917U, P4 = 668265263U, P5 = 374761393U;
@@ -65,7 +67,7 @@ size_t oracle_lz4f_compress(const uint8_t* src, size_t n, uint8_t* dst, size_t c
     *op = (uint8_t)(oracle_xxh32(desc, (size_t)(op - desc), 0) >> 8); op++;
     for (size_t off = 0; off < n; off += bsz) {
         const size_t part = n - off < bsz ? n - off : bsz;
-        int c = oracle_lz4_compress(src + off, (int)part, op + 4, (int)part - 1);      /* :747 dstCapacity = srcSize-1 */
+        int c = oracle_lz4_compress(src + off, (int)part, op + 4, (int)part - 1);      /* lz4/lz4frame.c:747 dstCapacity = srcSize-1 */
         if (c <= 0) { wr32le(op, (uint32_t)part | 0x80000000U); memcpy(op + 4, src + off, part); op += 4 + part; }
         else { wr32le(op, (uint32_t)c); op += 4 + (size_t)c; }
     }

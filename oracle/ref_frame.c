@@ -1,7 +1,7 @@
 /*
  * oracle/ref_frame.c -- TEST INFRASTRUCTURE.  Thin shim around the reference's own lz4frame.c (compiled from the
  * reference tree into oracle/_ref/liblz4fref.so by oracle/Makefile) so the tests can make and read LZ4 frames with
- * the reference implementation: LZ4F_compressFrame (lz4/lz4frame.c:398-470) and LZ4F_decompress (:1372-1750).
+ * the reference implementation: LZ4F_compressFrame (lz4/lz4frame.c:429-470) and LZ4F_decompress (lz4/lz4frame.c:1384-1830).
  */
 #include <stddef.h>
 #include <string.h>
