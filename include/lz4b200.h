@@ -134,7 +134,7 @@ int64_t lzbench_lz4_b200_decompress_batch(const size_t* chunk_sizes, const size_
                                           char* in, char* out, char* workmem);
 
 /* ---- PCIe yardstick -------------------------------------------------
- * What the reference's `cudaMemcpy` row does (lzbench_cuda_memcpy, _lzbench/compressors.cpp:1826-1831): n bytes host ->
+ * What the reference's `cudaMemcpy` row does (lzbench_cuda_memcpy, _lzbench/compressors.cpp:1828-1833): n bytes host ->
  * device -> host, no kernel, through this library's staging (page-locked buffers, overlapped slices).  Returns n. */
 int64_t lz4b200_memcpy_batch(lz4b200_ctx* ctx, const char* in, size_t n, char* out);
 

@@ -749,7 +749,7 @@ int64_t lz4b200_decompress_batch(lz4b200_ctx* c, const char* in, const size_t* c
 }
 
 // The yardstick for e2e: what the reference's `cudaMemcpy` row measures (lzbench_cuda_memcpy,
-// _lzbench/compressors.cpp:1826-1831: H2D then D2H of the same bytes), through this library's plumbing -- page-locked
+// _lzbench/compressors.cpp:1828-1833: H2D then D2H of the same bytes), through this library's plumbing -- page-locked
 // caller buffers, slices on the pipeline streams so the two directions overlap.  No kernel runs.
 int64_t lz4b200_memcpy_batch(lz4b200_ctx* c, const char* in, size_t n, char* out)
 {
