@@ -89,6 +89,7 @@ struct lz4b200_ctx {
     int compress_gen = 2;               // compress: 0 warp per chunk, 1 CTA per chunk (parallel match finder + speculative parse), 2 = 1 with the phases on two warp groups (default)
     int team = 0;                       // lanes per chunk for the team decoders: 8 / 16 / 32, 0 = by batch size
     int slices = 0;                     // host entry points: number of pipeline slices (0 = automatic)
+    bool own_h2d = true;                // inbound bulk copies on their own stream (option "h2d" = "own" / "shared")
     bool host_register = false;         // page-lock caller buffers on first sight (lzbench's are plain malloc)
     struct Reg { const char* p; size_t n; };
     Reg regs[16] = {};
@@ -98,7 +99,8 @@ struct lz4b200_ctx {
     static constexpr int MAX_SLICES = 64;
     cudaStream_t streams[NS] = {};
     cudaStream_t d2h_stream = nullptr;
-    cudaEvent_t ev_sizes = nullptr, ev_scan[MAX_SLICES] = {}, ev_done[MAX_SLICES] = {};
+    cudaStream_t h2d_stream = nullptr;  // ALL inbound bulk copies: spread over the compute streams they lose a third of the link (measured: 1 GiB each way in 32 ms on 8 streams, 22.6 ms on one)
+    cudaEvent_t ev_sizes = nullptr, ev_scan[MAX_SLICES] = {}, ev_done[MAX_SLICES] = {}, ev_in[MAX_SLICES] = {};
     uint64_t launches = 0;
     // optional per-launch timing of the dominant (codec) kernel: event pairs on the launching stream
     bool timing = false;
@@ -413,6 +415,7 @@ int ensure_events(lz4b200_ctx* c, int K)
     for (int k = 0; k < K; k++) {
         if (!c->ev_scan[k]) CU(cudaEventCreateWithFlags(&c->ev_scan[k], cudaEventDisableTiming));
         if (!c->ev_done[k]) CU(cudaEventCreateWithFlags(&c->ev_done[k], cudaEventDisableTiming));
+        if (!c->ev_in[k]) CU(cudaEventCreateWithFlags(&c->ev_in[k], cudaEventDisableTiming));
     }
     return 0;
 }
@@ -468,6 +471,9 @@ int lz4b200_create(int device, size_t max_total_bytes, size_t max_chunk_bytes, l
         cudaError_t e = cudaStreamCreateWithFlags(&c->streams[i], cudaStreamNonBlocking);
         if (e != cudaSuccess) { lz4b200_destroy(c); return fail(-2, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
     }
+    if (cudaStreamCreateWithFlags(&c->h2d_stream, cudaStreamNonBlocking) != cudaSuccess) {
+        lz4b200_destroy(c); return fail(-2, "cudaStreamCreate failed");
+    }
     if (cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking) != cudaSuccess) {
         lz4b200_destroy(c); return fail(-2, "cudaStreamCreate failed");
     }
@@ -498,10 +504,12 @@ void lz4b200_destroy(lz4b200_ctx* c)
     for (int i = 0; i < c->n_regs; i++) cudaHostUnregister(const_cast<char*>(c->regs[i].p));
     for (int i = 0; i < lz4b200_ctx::NS; i++) if (c->streams[i]) cudaStreamDestroy(c->streams[i]);
     if (c->d2h_stream) cudaStreamDestroy(c->d2h_stream);
+    if (c->h2d_stream) cudaStreamDestroy(c->h2d_stream);
     if (c->ev_sizes) cudaEventDestroy(c->ev_sizes);
     for (int i = 0; i < lz4b200_ctx::MAX_SLICES; i++) {
         if (c->ev_scan[i]) cudaEventDestroy(c->ev_scan[i]);
         if (c->ev_done[i]) cudaEventDestroy(c->ev_done[i]);
+        if (c->ev_in[i]) cudaEventDestroy(c->ev_in[i]);
     }
     c->usz.release(); c->csz.release(); c->uoff.release(); c->coff.release();
     c->scalars.release(); c->status.release(); c->stage.release(); c->seg64.release(); c->seg32.release();
@@ -540,6 +548,7 @@ int lz4b200_set_option(lz4b200_ctx* c, const char* key, const char* value)
         int d = atoi(value);
         if (d >= 2 && d <= 4) { v6_depth() = d; return 0; }
     }
+    if (!strcmp(key, "h2d")) { c->own_h2d = strcmp(value, "shared") != 0; return 0; }
     if (!strcmp(key, "host_register")) { c->host_register = value[0] == '1'; return 0; }
     if (!strcmp(key, "slices")) {
         int k = atoi(value);
@@ -658,7 +667,11 @@ static int64_t compress_batch_impl(lz4b200_ctx* c, const char* in, const size_t*
         size_t bytes = 0;
         for (size_t i = f; i < f + m; i++) bytes += chunk_sizes[i];
         CU(cudaStreamWaitEvent(st, c->ev_sizes, 0));
-        CU(cudaMemcpyAsync((u8*)c->d_plain.p + in_off, in + in_off, bytes, cudaMemcpyHostToDevice, st));
+        // inbound copies on their own stream, except for frames: measured on one box (scripts/h2d_ab.py, 1 GiB, six runs)
+        // chunked compress 24.1-24.7 ms own vs 24.4-25.5 shared, frame compress 24.6-30.6 (erratic) own vs 24.4-25.8 shared
+        const bool own = c->own_h2d && !frame;
+        CU(cudaMemcpyAsync((u8*)c->d_plain.p + in_off, in + in_off, bytes, cudaMemcpyHostToDevice, own ? c->h2d_stream : st));
+        if (own) { CU(cudaEventRecord(c->ev_in[k], c->h2d_stream)); CU(cudaStreamWaitEvent(st, c->ev_in[k], 0)); }
         int rc = compress_slice(c, (const u8*)c->d_plain.p + in_off, (const u64*)c->usz.p + f, m, max_chunk,
                                 (u8*)c->d_packed.p, (u64*)c->csz.p + f, k ? running + (k - 1) : (frame ? fbase : nullptr), running + k,
                                 scratch_at(c, f, stride, k), st, k ? c->ev_scan[k - 1] : nullptr, c->ev_scan[k], frame, c->d_mirror + k);
@@ -732,7 +745,8 @@ int64_t lz4b200_decompress_batch(lz4b200_ctx* c, const char* in, const size_t* c
         size_t ub = 0, cb = 0;
         for (size_t i = f; i < f + m; i++) { ub += chunk_sizes[i]; cb += compr_sizes[i]; }
         CU(cudaStreamWaitEvent(st, c->ev_sizes, 0));
-        CU(cudaMemcpyAsync((u8*)c->d_packed.p + coff, in + coff, cb, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync((u8*)c->d_packed.p + coff, in + coff, cb, cudaMemcpyHostToDevice, c->own_h2d ? c->h2d_stream : st));
+        if (c->own_h2d) { CU(cudaEventRecord(c->ev_in[k], c->h2d_stream)); CU(cudaStreamWaitEvent(st, c->ev_in[k], 0)); }
         int rc = decompress_slice(c, (const u8*)c->d_packed.p + coff, (const u64*)c->csz.p + f, (const u64*)c->usz.p + f,
                                   m, max_chunk, (u8*)c->d_plain.p + uoff, d_bad, scratch_at(c, f, 0, k), st);
         if (rc) { cudaDeviceSynchronize(); return rc; }
@@ -764,7 +778,7 @@ int64_t lz4b200_memcpy_batch(lz4b200_ctx* c, const char* in, size_t n, char* out
     if (int rc = ensure_events(c, K)) return rc;
     for (int k = 0; k < K; k++) {
         const size_t lo = n * k / K, hi = n * (k + 1) / K;
-        cudaStream_t st = c->streams[k % lz4b200_ctx::NS];
+        cudaStream_t st = c->h2d_stream;
         CU(cudaMemcpyAsync((u8*)c->d_plain.p + lo, in + lo, hi - lo, cudaMemcpyHostToDevice, st));
         CU(cudaEventRecord(c->ev_done[k], st));
         CU(cudaStreamWaitEvent(c->d2h_stream, c->ev_done[k], 0));
@@ -897,7 +911,8 @@ int64_t lz4b200_frame_decompress(lz4b200_ctx* c, const char* in, size_t in_size,
         const size_t f = first[k], m = first[k + 1] - first[k];
         const size_t lo = pos[f] - 4, hi = pos[f + m - 1] + (words[f + m - 1] & ~F_RAW) + bx;
         CU(cudaStreamWaitEvent(st, c->ev_sizes, 0));
-        CU(cudaMemcpyAsync((u8*)c->d_packed.p + lo, in + lo, hi - lo, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync((u8*)c->d_packed.p + lo, in + lo, hi - lo, cudaMemcpyHostToDevice, c->own_h2d ? c->h2d_stream : st));
+        if (c->own_h2d) { CU(cudaEventRecord(c->ev_in[k], c->h2d_stream)); CU(cudaStreamWaitEvent(st, c->ev_in[k], 0)); }
         u64 *csz_k = (u64*)c->csz.p + f, *usz_k = (u64*)c->usz.p + f;
         frame_block_sizes_kernel<<<(unsigned)((m + FS_WARPS - 1) / FS_WARPS), FS_WARPS * 32, 0, st>>>(
             (const u8*)c->d_packed.p, frame_bytes, d_pos + f, (const u32*)c->fhdr.p + f, csz_k, usz_k, (u32)m,
