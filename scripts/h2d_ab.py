@@ -20,10 +20,10 @@ def t(fn, reps=6):
     for _ in range(reps): fn()
     return (time.perf_counter() - t0) / reps * 1e3
 for rnd in range(3):
-    for mode in ("shared", "own"):
-        ctx.set_option("h2d", mode)
+    for mode in ("0", "1"):
+        ctx.set_option("ramp", mode)
         td = t(lambda: ctx.decompress_batch(h_packed, compr, cs, h_back))
         tc = t(lambda: ctx.compress_batch(h_plain, cs, h_out))
         tfc = t(lambda: ctx.frame_compress(h_plain.numpy(), 4, outbuf=h_frame.numpy()))
         tfd = t(lambda: L.lib.lz4b200_frame_decompress(ctx._h, f2.ctypes.data, f2.nbytes, h_back.numpy().ctypes.data, n, 0))
-        print(f"h2d={mode}: decompress {td:.1f} ms  compress {tc:.1f} ms  frame compress {tfc:.1f} ms  frame decompress {tfd:.1f} ms", flush=True)
+        print(f"ramp={mode}: decompress {td:.1f} ms  compress {tc:.1f} ms  frame compress {tfc:.1f} ms  frame decompress {tfd:.1f} ms", flush=True)
