@@ -109,7 +109,8 @@ int lz4b200_debug_prof(lz4b200_ctx* ctx, uint64_t* out16);
  * its load, no barriers on the fast path), "v4" (v3 with a warp-uniform, predicated fast path; default);
  * "team" = "8"/"16" lanes per chunk (v2 also "4"/"32").  "compress" = "v0"/"v1" picks the compressor generation; "slices" = number of H2D/kernel/D2H
  * pipeline slices of the host entry points (0 = automatic); "host_register" = "1" page-locks caller
- * buffers on first sight (what the lzbench wrappers turn on).  Also "timing" = "0"/"1" (see above).  Returns 0, or -1 for an unknown key or value.
+ * buffers on first sight (what the lzbench wrappers turn on).  "accel" = LZ4_compress_fast's acceleration (lz4/lz4.c:1352-1375; the lz4fast levels of lzbench, _lzbench/compressors.cpp:348-356):
+ * 1 default, 2-3 probe every 2nd position, >= 4 every 4th.  Also "timing" = "0"/"1" (see above).  Returns 0, or -1 for an unknown key or value.
  * Default kernels: the fastest verified generation. */
 int lz4b200_set_option(lz4b200_ctx* ctx, const char* key, const char* value);
 

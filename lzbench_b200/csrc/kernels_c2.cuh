@@ -97,7 +97,7 @@ __device__ __forceinline__ u32 c2_block_excl(u32 v, u32* warp_scratch, u32& tota
     return excl;
 }
 
-template <int MODE>
+template <int MODE, int ACC>
 __global__ void __launch_bounds__(C2_THREADS, 2)
 compress_c2_kernel(const u8* __restrict__ in, const u64* __restrict__ in_off, const u64* __restrict__ usz,
                    u8* __restrict__ stage, u64 slot_stride, u64* __restrict__ csz, u32 n_chunks_arg, u32* ticket,
@@ -182,48 +182,95 @@ compress_c2_kernel(const u8* __restrict__ in, const u64* __restrict__ in_off, co
                     const long long a0 = prof ? clock64() : 0;
                     if (t >= 2) c2_bar_sync(3, buf);          // group B has released this buffer
                     const long long a1 = prof ? clock64() : 0;
+                    if (ACC == 1) {
                     // ---- M: match finding over the tile, 256 positions per batch ----
-                    for (u32 b = 0; b < C1_TILE; b += C2_GROUP) {
-                        const u32 p = t0 + b + gtid;
-                        const bool valid = p <= mfl;
-                        u32 v = 0, h = 0x10000u + lane, cand = 0;
-                        if (valid) { v = c1_rd32(s_in + p); h = hash13(v); cand = s_tab[h]; }
-                        // batch-local first occurrence: the main table is a batch behind, so a repeat at distance < 256 inside this
-                        // batch would be missed (measured on real binaries / source text: +6..7 % size).  Every position of the
-                        // batch posts itself to a 512-bucket table with atomicMax(tag | ~pos): the tag makes entries of older
-                        // batches lose without clearing, the inverted position makes the FIRST occurrence of the batch win.
-                        const u32 tag = ((t0 + b) / C2_GROUP + 1u) << 16;
-                        if (valid) atomicMax(&s_lt[h & (C1_LT - 1)], tag | (0xFFFFu - p));
-                        C2_BAR_A();
-                        bool ok = false;
-                        {
-                            u32 near = 0;                         // same 4 bytes d lanes earlier in this warp (short periods)
-                            if (MODE == 0) {
-                                const unsigned peers = __match_any_sync(FULL, h);
-                                const unsigned lower = peers & ((1u << lane) - 1u);
-                                if (lower) near = lane - (31 - __clz(lower));
-                            } else if (MODE == 1) {
-                                #pragma unroll
-                                for (u32 d : {16u, 8u, 4u, 3u, 2u, 1u}) {
-                                    const u32 y = __shfl_up_sync(FULL, v, d);
-                                    if (lane >= d && y == v) near = d;
+                        for (u32 b = 0; b < C1_TILE; b += C2_GROUP) {
+                            const u32 p = t0 + b + gtid;
+                            const bool valid = p <= mfl;
+                            u32 v = 0, h = 0x10000u + lane, cand = 0;
+                            if (valid) { v = c1_rd32(s_in + p); h = hash13(v); cand = s_tab[h]; }
+                            // batch-local first occurrence: the main table is a batch behind, so a repeat at distance < 256 inside this
+                            // batch would be missed (measured on real binaries / source text: +6..7 % size).  Every position of the
+                            // batch posts itself to a 512-bucket table with atomicMax(tag | ~pos): the tag makes entries of older
+                            // batches lose without clearing, the inverted position makes the FIRST occurrence of the batch win.
+                            const u32 tag = ((t0 + b) / C2_GROUP + 1u) << 16;
+                            if (valid) atomicMax(&s_lt[h & (C1_LT - 1)], tag | (0xFFFFu - p));
+                            C2_BAR_A();
+                            bool ok = false;
+                            {
+                                u32 near = 0;                         // same 4 bytes d lanes earlier in this warp (short periods)
+                                if (MODE == 0) {
+                                    const unsigned peers = __match_any_sync(FULL, h);
+                                    const unsigned lower = peers & ((1u << lane) - 1u);
+                                    if (lower) near = lane - (31 - __clz(lower));
+                                } else if (MODE == 1) {
+                                    #pragma unroll
+                                    for (u32 d : {16u, 8u, 4u, 3u, 2u, 1u}) {
+                                        const u32 y = __shfl_up_sync(FULL, v, d);
+                                        if (lane >= d && y == v) near = d;
+                                    }
+                                }
+                                if (valid) {
+                                    const u32 lt = s_lt[h & (C1_LT - 1)];
+                                    const u32 q = 0xFFFFu - (lt & 0xFFFFu);               // first position of this batch in my bucket
+                                    const bool local = (lt >> 16) == (tag >> 16) && q < p;
+                                    const u32 main_cand = cand;
+                                    if (near) cand = p - near; else if (local) cand = q;
+                                    ok = cand < p && c1_rd32(s_in + cand) == v;
+                                    if (!ok && cand != main_cand) { cand = main_cand; ok = cand < p && c1_rd32(s_in + cand) == v; }
+                                    s_tab[h] = (u16)p;                                     // racing lanes: any winner is a valid candidate
                                 }
                             }
+                            mo[b + gtid] = ok ? (u16)(p - cand) : (u16)0;
+                            const unsigned hit = __ballot_sync(FULL, ok);
+                            if (lane == 0) bi[(b + gtid) >> 5] = hit;
+                            C2_BAR_A();
+                        }
+    
+                    } else {
+                        // ---- M, lz4fast levels (LZ4_compress_fast's acceleration, lz4/lz4.c:1352-1375): every position is still
+                        //      posted and inserted (cheap), but only every ACC-th one is PROBED (the expensive part: candidate
+                        //      choice, verification) -- the same density of match attempts as the reference's constant skip
+                        //      step, on a fixed grid.  A batch is 256 * ACC positions, one probe per thread.
+                        for (u32 b = 0; b < C1_TILE; b += C2_GROUP * ACC) {
+                            const u32 p = t0 + b + gtid * ACC;              // the probed position
+                            const bool valid = p <= mfl;
+                            const u32 tag = ((t0 + b) / (C2_GROUP * ACC) + 1u) << 16;
+                            u32 v = 0, h = 0, cand = 0;
+                            #pragma unroll
+                            for (u32 i = 0; i < (u32)ACC; i++) {
+                                if (p + i <= mfl) {
+                                    const u32 vi = c1_rd32(s_in + p + i), hi = hash13(vi);
+                                    if (i == 0) { v = vi; h = hi; cand = s_tab[hi]; }
+                                    atomicMax(&s_lt[hi & (C1_LT - 1)], tag | (0xFFFFu - (p + i)));
+                                }
+                            }
+                            C2_BAR_A();
+                            bool ok = false;
                             if (valid) {
                                 const u32 lt = s_lt[h & (C1_LT - 1)];
                                 const u32 q = 0xFFFFu - (lt & 0xFFFFu);               // first position of this batch in my bucket
                                 const bool local = (lt >> 16) == (tag >> 16) && q < p;
                                 const u32 main_cand = cand;
-                                if (near) cand = p - near; else if (local) cand = q;
+                                if (local) cand = q;
                                 ok = cand < p && c1_rd32(s_in + cand) == v;
                                 if (!ok && cand != main_cand) { cand = main_cand; ok = cand < p && c1_rd32(s_in + cand) == v; }
-                                s_tab[h] = (u16)p;                                     // racing lanes: any winner is a valid candidate
                             }
+                            #pragma unroll
+                            for (u32 i = 0; i < (u32)ACC; i++)
+                                if (p + i <= mfl) s_tab[hash13(c1_rd32(s_in + p + i))] = (u16)(p + i);
+                            mo[b + gtid * ACC] = ok ? (u16)(p - cand) : (u16)0;
+                            const unsigned hit = __ballot_sync(FULL, ok);
+                            if (lane < (u32)ACC) {                               // the warp's 32 probes cover ACC words of the bit map
+                                constexpr u32 PER = 32 / ACC;
+                                const u32 sub = (hit >> (lane * PER)) & ((1u << PER) - 1u);
+                                u32 word = 0;
+                                #pragma unroll
+                                for (u32 k = 0; k < PER; k++) word |= ((sub >> k) & 1u) << (k * ACC);
+                                bi[(b >> 5) + warp * ACC + lane] = word;
+                            }
+                            C2_BAR_A();
                         }
-                        mo[b + gtid] = ok ? (u16)(p - cand) : (u16)0;
-                        const unsigned hit = __ballot_sync(FULL, ok);
-                        if (lane == 0) bi[(b + gtid) >> 5] = hit;
-                        C2_BAR_A();
                     }
 
                     __threadfence_block();
@@ -411,13 +458,13 @@ compress_c2_kernel(const u8* __restrict__ in, const u64* __restrict__ in_off, co
     }
 }
 
-template <int MODE>
+template <int MODE, int ACC>
 inline cudaError_t c2_launch_mode(const u8* in, const u64* in_off, const u64* usz, u8* stage, u64 stride, u64* csz,
                                   u32 n, u32* ticket, int sm_count, cudaStream_t st, const u64* n_dev, u32* tail_pos, u32* tail_len, const u32* hist, u64* prof)
 {
     static bool attr = false;
     if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(compress_c2_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t e = cudaFuncSetAttribute(compress_c2_kernel<MODE, ACC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)C2Smem::BYTES);
         if (e != cudaSuccess) return e;
         attr = true;
@@ -426,18 +473,24 @@ inline cudaError_t c2_launch_mode(const u8* in, const u64* in_off, const u64* us
     if (grid > n) grid = n;
     cudaError_t e = cudaMemsetAsync(ticket, 0, sizeof(u32), st);
     if (e != cudaSuccess) return e;
-    compress_c2_kernel<MODE><<<grid, C2_THREADS, C2Smem::BYTES, st>>>(in, in_off, usz, stage, stride, csz, n, ticket, n_dev, tail_pos, tail_len, hist, prof);
+    compress_c2_kernel<MODE, ACC><<<grid, C2_THREADS, C2Smem::BYTES, st>>>(in, in_off, usz, stage, stride, csz, n, ticket, n_dev, tail_pos, tail_len, hist, prof);
     return cudaGetLastError();
 }
 
 inline cudaError_t c2_launch_compress(const u8* in, const u64* in_off, const u64* usz, u8* stage, u64 stride, u64* csz,
                                       u32 n, u32* ticket, int sm_count, cudaStream_t st, const u64* n_dev = nullptr,
-                                      u32* tail_pos = nullptr, u32* tail_len = nullptr, const u32* hist = nullptr, u64* prof = nullptr)
+                                      u32* tail_pos = nullptr, u32* tail_len = nullptr, const u32* hist = nullptr, u64* prof = nullptr,
+                                      u32 accel = 1)
 {
+    // acceleration (lz4fast levels): probe grid of 2 (accel 2-3) or 4 (accel >= 4) positions.  A grid of 8 was measured:
+    // 133 GB/s but 6.8 % larger than the reference at accel 8, while the grid of 4 is SMALLER than the reference from
+    // accel 8 on (66.0 % vs 70.4 %) at 127 GB/s.  The match-finding modes 0 / 1 exist only at acceleration 1.
+    if (accel >= 4) return c2_launch_mode<2, 4>(in, in_off, usz, stage, stride, csz, n, ticket, sm_count, st, n_dev, tail_pos, tail_len, hist, prof);
+    if (accel >= 2) return c2_launch_mode<2, 2>(in, in_off, usz, stage, stride, csz, n, ticket, sm_count, st, n_dev, tail_pos, tail_len, hist, prof);
     switch (c1_mode()) {
-    case 0:  return c2_launch_mode<0>(in, in_off, usz, stage, stride, csz, n, ticket, sm_count, st, n_dev, tail_pos, tail_len, hist, prof);
-    case 2:  return c2_launch_mode<2>(in, in_off, usz, stage, stride, csz, n, ticket, sm_count, st, n_dev, tail_pos, tail_len, hist, prof);
-    default: return c2_launch_mode<1>(in, in_off, usz, stage, stride, csz, n, ticket, sm_count, st, n_dev, tail_pos, tail_len, hist, prof);
+    case 0:  return c2_launch_mode<0, 1>(in, in_off, usz, stage, stride, csz, n, ticket, sm_count, st, n_dev, tail_pos, tail_len, hist, prof);
+    case 2:  return c2_launch_mode<2, 1>(in, in_off, usz, stage, stride, csz, n, ticket, sm_count, st, n_dev, tail_pos, tail_len, hist, prof);
+    default: return c2_launch_mode<1, 1>(in, in_off, usz, stage, stride, csz, n, ticket, sm_count, st, n_dev, tail_pos, tail_len, hist, prof);
     }
 }
 

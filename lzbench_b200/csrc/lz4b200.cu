@@ -87,6 +87,7 @@ struct lz4b200_ctx {
     int sm_count = 148;
     int kernel_gen = 5;                 // decode: 0 warp per chunk, 1 CTA tile (TMA), 2 sub-warp teams, 3 + mapped lanes / pipelined match, 4 + warp-uniform fast path, 5 + compressed stream through a cp.async ring, long literal runs on the common path (default), 6 = 5 with cp.async-staged deep match pipeline (experiment)
     int compress_gen = 2;               // compress: 0 warp per chunk, 1 CTA per chunk (parallel match finder + speculative parse), 2 = 1 with the phases on two warp groups (default)
+    int accel = 1;                      // compress: LZ4_compress_fast's acceleration (1 = lz4 default; lz4fast levels), probe grid 1/2/4/8
     int team = 0;                       // lanes per chunk for the team decoders: 8 / 16 / 32, 0 = by batch size
     int slices = 0;                     // host entry points: number of pipeline slices (0 = automatic)
     bool ramp = true;                   // decompress slice plan: small first slices (option "ramp")
@@ -245,12 +246,13 @@ int compress_slice(lz4b200_ctx* c, const u8* d_in, const u64* d_usz, size_t n, s
         scan_sizes_kernel<<<1, SCAN_THREADS, 0, st>>>(js, none, (u64)n);
         seg_fill_kernel<<<gb, 256, 0, st>>>(d_usz, s.uoff, sa, (u32)n);
         CU(c2_launch_compress(d_in, sa.job_in_off, sa.job_len, s.stage, slot_stride_for(SEG_BYTES), sa.job_csz,
-                              (u32)jobs_max, s.ticket, c->sm_count, st, sa.n_jobs, sa.job_tail_pos, sa.job_tail_len, sa.job_hist));
+                              (u32)jobs_max, s.ticket, c->sm_count, st, sa.n_jobs, sa.job_tail_pos, sa.job_tail_len, sa.job_hist, nullptr,
+                              (u32)c->accel));
         seg_stitch_size_kernel<<<gb, 256, 0, st>>>(sa, s.stage, slot_stride_for(SEG_BYTES), d_csz, (u32)n);
         c->launches += 5;
     } else if (c->compress_gen == 2 && c1_compress_supported(max_chunk)) {
         CU(c2_launch_compress(d_in, s.uoff, d_usz, s.stage, stride, d_csz, (u32)n, s.ticket, c->sm_count, st, nullptr, nullptr, nullptr,
-                              nullptr, c->prof_on ? (u64*)c->prof.p : nullptr));
+                              nullptr, c->prof_on ? (u64*)c->prof.p : nullptr, (u32)c->accel));
         c->launches++;
     } else if (c->compress_gen == 1 && c1_compress_supported(max_chunk)) {
         CU(c1_launch_compress(d_in, s.uoff, d_usz, s.stage, stride, d_csz, (u32)n, s.ticket,
@@ -552,6 +554,11 @@ int lz4b200_set_option(lz4b200_ctx* c, const char* key, const char* value)
         if (!strcmp(value, "v2")) { c->compress_gen = 2; return 0; }
     }
     if (!strcmp(key, "c1mode")) { c1_mode() = atoi(value); return 0; }
+    if (!strcmp(key, "accel")) {                        // LZ4_compress_fast's acceleration (lz4/lz4.c:1352-1375); the lz4fast levels of lzbench
+        int a = atoi(value);
+        c->accel = a < 1 ? 1 : (a > 65537 ? 65537 : a);
+        return 0;
+    }
     if (!strcmp(key, "team")) {
         int t = atoi(value);
         if (t == 0 || t == 4 || t == 8 || t == 16 || t == 32) { c->team = t; return 0; }

@@ -19,7 +19,7 @@ extern "C" {
 
 char* lzbench_lz4_b200_init(size_t insize, size_t level, size_t param2)
 {
-    (void)level; (void)param2;
+    (void)param2;
     Workmem* w = new Workmem();
     // insize is min(-b chunk, file size) (_lzbench/lzbench.cpp:344,350): a chunk-size hint only.
     if (lz4b200_create(0, 0, insize, &w->ctx) != 0) {
@@ -31,6 +31,9 @@ char* lzbench_lz4_b200_init(size_t insize, size_t level, size_t param2)
     // (opt out with LZ4B200_HOST_REGISTER=0)
     const char* hr = getenv("LZ4B200_HOST_REGISTER");
     lz4b200_set_option(w->ctx, "host_register", (hr && hr[0] == '0') ? "0" : "1");
+    // a row with levels hands LZ4_compress_fast's acceleration down as `level` (the lz4fast rows,
+    // _lzbench/compressors.cpp:348-356); the plain lz4_b200 row has level 0 = acceleration 1
+    if (level > 1) { char buf[24]; snprintf(buf, sizeof buf, "%zu", level); lz4b200_set_option(w->ctx, "accel", buf); }
     return reinterpret_cast<char*>(w);
 }
 

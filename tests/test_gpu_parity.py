@@ -287,3 +287,31 @@ def test_many_small_files_mode(gpu_ctx):
                 rr, o = O.oracle_decompress(blk, u)
                 assert rr == u and np.array_equal(o, plain)
 
+
+
+@pytest.mark.parametrize("accel", [2, 4, 8, 33])
+def test_lz4fast_acceleration_levels(gpu_ctx, accel):
+    """`accel` = LZ4_compress_fast's acceleration (the lz4fast rows, _lzbench/compressors.cpp:348-356).
+    Same bars as level 1, measured against the reference at the same acceleration."""
+    n = 4 << 20
+    try:
+        for kind, seed in CORPORA:
+            data = L.corpus(kind, n, seed=seed)
+            for chunk in (4096, 65536, 1 << 20):
+                cs = L.chunk_list(n, chunk)
+                gpu_ctx.set_option("accel", str(accel))
+                packed, compr, total = gpu_ctx.compress_batch(data, cs)
+                out, r = gpu_ctx.decompress_batch(packed[:total], compr, cs)
+                assert r == n and np.array_equal(out, data)
+                check_gpu_blocks_with_reference(data[:4 * chunk], packed, compr[:4], cs[:4])
+                ref_total = 0
+                tmp = np.empty(L.compress_bound(chunk), dtype=np.uint8)
+                for i, u in enumerate(cs.tolist()):
+                    part = data[i * chunk:i * chunk + int(u)]
+                    z = O.orc.oracle_lz4_compress_fast(part.ctypes.data, len(part), tmp.ctypes.data, len(tmp), accel)
+                    ref_total += min(z, len(part))                   # lzbench stores a chunk raw when it does not shrink
+                # + 4 bytes per chunk: on all-zero 4 KiB chunks the first probed grid position costs up to three more
+                # literals than the reference's first match at position 1 (27 / 29 vs 26 bytes per chunk)
+                assert total <= RATIO_TOLERANCE * ref_total + 4 * len(cs), (kind, chunk, accel, total, ref_total)
+    finally:
+        gpu_ctx.set_option("accel", "1")
