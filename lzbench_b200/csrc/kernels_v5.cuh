@@ -223,8 +223,9 @@ __global__ void __launch_bounds__(V2_BLOCK, 7)     // <= 72 registers: 28 warps 
 decompress_v5_kernel(const __grid_constant__ V5Params P)
 {
     const u32 lane = lane_id();
-    const u32 j = lane & (T - 1);
-    const u32 tbase = lane & ~(T - 1);
+    u32 j = lane & (T - 1);
+    u32 tbase = lane & ~(T - 1);
+    asm volatile("" : "+r"(j), "+r"(tbase));           // keep them in registers: ptxas otherwise re-reads SR_TID.X three times per iteration
     constexpr u32 NX = (16 + T - 1) / T;               // literal bytes per lane (runs of <= 14 on the common path)
     constexpr u32 NM = (18 + T - 1) / T;               // bytes of a short match (<= 18) per lane
     constexpr u32 SEG = 16 * T, RING = 4 * SEG;        // one cp.async of 16 bytes per lane fills a segment
