@@ -238,6 +238,7 @@ decompress_v5_kernel(const __grid_constant__ V5Params P)
     // ts.src is the chunk start rounded DOWN to 16 bytes, and ip / ts.clen / ip_safe count from there (the first
     // token is at ip = chunk start & 15): stream byte p is ring[p % RING], segment g is the 16-aligned ts.src + g*SEG
     bool busy = false, exhausted = false;
+    bool first = true;                                 // the first pass goes through the cold function to fetch the first chunks
     u8* dst = nullptr;
     u32 ip = 0, op = 0;
     u32 tok = 0;                                       // token at stream position ip
@@ -344,7 +345,10 @@ decompress_v5_kernel(const __grid_constant__ V5Params P)
         }
 
         // ---- everything else, behind one vote and one call ----
-        if (!__any_sync(FULL, (busy && !f) || (!busy && !exhausted))) continue;
+        // a team that is not busy here has run out of chunks (the cold function hands out the next chunk or marks the team
+        // exhausted before it returns), so only busy teams can ask for it
+        if (!__any_sync(FULL, busy && !f) && !first) continue;
+        first = false;
         V5State S{ dst, ip, op, tok, pm_len, op_safe, ip_safe, rem, busy, exhausted, fastable, lrem };
         const bool done = v5_cold<T>(S, f, P, ring, ts);
         dst = S.dst; ip = S.ip; op = S.op; tok = S.tok; pm_len = S.pm_len; op_safe = S.op_safe; ip_safe = S.ip_safe;
