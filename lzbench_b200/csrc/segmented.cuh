@@ -20,6 +20,7 @@ namespace lz4b200 {
 
 constexpr u32 SEG_BYTES = 65536;                 // bytes a job holds in shared memory
 constexpr u32 SEG_HIST = 16384;                  // of which history: the previous 16 KiB of the chunk, match source only
+constexpr u32 SEG_TAIL_MIN = 16;                  // fewest new bytes the last segment of a chunk may hold
 constexpr u32 SEG_NEW = SEG_BYTES - SEG_HIST;    // and new data, which the job encodes
 
 struct SegArrays {
@@ -50,10 +51,15 @@ __global__ void seg_fill_kernel(const u64* __restrict__ usz, const u64* __restri
     const u32 c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= n_chunks) return;
     const u64 n = usz[c], base = a.job_base[c], cnt = a.jobs_per_chunk[c];
+    // An inner segment may match right up to its last byte, so the chunk's end-of-block rules (last match starts >= 12 and
+    // ends >= 5 bytes before the end, lz4/lz4.c:883-884) rest on the LAST segment alone: it must not be shorter than 16 new
+    // bytes.  If the cut would leave fewer, the last boundary moves 16 bytes down (found by scripts/fuzz_gpu.py: a chunk of
+    // 49 153 bytes came out with one literal behind its last match).
+    const u64 shift = (cnt > 1 && n - (cnt - 1) * SEG_NEW < SEG_TAIL_MIN) ? SEG_TAIL_MIN : 0;
     for (u64 s = 0; s < cnt; s++) {
-        const u64 off = s * SEG_NEW;
+        const u64 off = s * SEG_NEW - (s + 1 == cnt ? shift : 0);
         const u32 hist = s ? SEG_HIST : 0;                     // SEG_NEW >= SEG_HIST: the history always exists
-        const u64 fresh = n - off < SEG_NEW ? n - off : SEG_NEW;
+        const u64 fresh = s + 1 == cnt ? n - off : SEG_NEW - (s + 2 == cnt ? shift : 0);
         a.job_in_off[base + s] = uoff[c] + off - hist;
         a.job_len[base + s] = hist + fresh;
         a.job_hist[base + s] = hist | (s + 1 < cnt ? 0x80000000u : 0u);   // bit 31: not the last segment of its chunk

@@ -315,3 +315,19 @@ def test_lz4fast_acceleration_levels(gpu_ctx, accel):
                 assert total <= RATIO_TOLERANCE * ref_total + 4 * len(cs), (kind, chunk, accel, total, ref_total)
     finally:
         gpu_ctx.set_option("accel", "1")
+
+
+def test_segment_boundary_chunk_sizes(gpu_ctx):
+    """Chunks larger than 64 KiB are compressed in 48 KiB segments whose inner ones may match up to their last byte; the
+    end-of-block rules of the whole chunk then rest on the last segment, which must not be tiny.  Found by
+    scripts/fuzz_gpu.py: a 49 153-byte chunk came out with a single literal behind its last match (rejected by
+    LZ4_decompress_safe).  Every size from a segment multiple to 20 bytes past it, on every corpus."""
+    sizes = [49152 * m + k for m in (1, 2, 3) for k in range(0, 21)] + [70000]      # 70000 forces the segmented path
+    cs = np.asarray(sizes, dtype=np.uint64)
+    n = int(cs.sum())
+    for kind, seed in CORPORA + [("mixed", 9)]:
+        data = L.corpus(kind, n, seed=seed)
+        packed, compr, total = gpu_ctx.compress_batch(data, cs)
+        check_gpu_blocks_with_reference(data, packed[:total], compr, cs)
+        out, r = gpu_ctx.decompress_batch(packed[:total], compr, cs)
+        assert r == n and np.array_equal(out, data)
