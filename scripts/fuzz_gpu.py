@@ -17,7 +17,7 @@ ACCEL = int(os.environ.get("FUZZ_ACCEL", "1"))
 ctx.set_option("accel", str(ACCEL))
 KINDS = ["mixed", "random", "repeat", "zero"]
 t_end = time.time() + secs
-rounds = blocks = corrupt = ratio_fail = 0
+rounds = blocks = corrupt = ratio_fail = frames_bad = 0
 while time.time() < t_end:
     # ---- a random mixture, random chunking ----
     parts = []; desc = []
@@ -28,7 +28,11 @@ while time.time() < t_end:
         parts.append(L.corpus(k, ln, seed=sd)); desc.append((k, ln, sd))
     data = np.concatenate(parts)
     n = len(data)
-    chunk = int(rng.choice([64, 1000, 4096, 16384, 65536, 100000, 262144, 1 << 20]))
+    chunk = int(rng.choice([13, 64, 1000, 4096, 16384, 65535, 65536, 65537, 65547, 100000, 262144, 1 << 20,
+                            49152 + int(rng.integers(0, 24)), 98304 + int(rng.integers(0, 24)), 65536 + int(rng.integers(0, 40))]))
+    if os.environ.get("FUZZ_ACCEL") is None:
+        ACCEL = int(rng.choice([1, 1, 1, 2, 4, 9]))
+        ctx.set_option("accel", str(ACCEL))
     if rng.random() < 0.3:                               # ragged list, lzbench -j style
         files = rng.integers(1, max(2, n // 3), int(rng.integers(1, 40)))
         files = files[np.cumsum(files) <= n]
@@ -54,7 +58,7 @@ while time.time() < t_end:
         ratio_fail += 1
     # every GPU block must be accepted by the oracle validator
     offp = 0; offu = 0
-    step = max(1, len(cs) // 50)
+    step = 1 if len(cs) <= 400 else max(1, len(cs) // 100)
     offs_p = np.concatenate([[0], np.cumsum(compr)]).astype(np.int64)
     offs_u = np.concatenate([[0], np.cumsum(cs)]).astype(np.int64)
     for i in range(0, len(cs), step):
@@ -93,5 +97,18 @@ while time.time() < t_end:
         assert rr == n and np.array_equal(oo, data), ("frame -> oracle", seed, rounds)
         rr, oo = ctx.frame_decompress(O.oracle_frame_compress(data, bid, 1, 1), n)
         assert rr == n and np.array_equal(oo, data), ("oracle frame -> gpu", seed, rounds, L.last_error())
+        # damaged frames: same verdict as the oracle, and when both accept, the same bytes
+        for _ in range(8):
+            g = f.copy()
+            for _ in range(int(rng.integers(1, 4))):
+                g[int(rng.integers(0, len(g)))] ^= 1 << int(rng.integers(0, 8))
+            if rng.random() < 0.2: g = g[:int(rng.integers(1, len(g)))].copy()
+            ro, oo = O.oracle_frame_decompress(g, n + 8)
+            rg, og = ctx.frame_decompress(g, n + 8)
+            if ro == O.BAD:
+                assert rg < 0, ("damaged frame accepted", seed, rounds, rg)
+            else:
+                assert rg == ro and np.array_equal(og, oo), ("damaged frame verdict", seed, rounds, rg, ro, L.last_error())
+            frames_bad += 1
     rounds += 1
-print(f"fuzz {'ok' if not ratio_fail else 'RATIO FAILURES ' + str(ratio_fail)}: {rounds} rounds, {blocks} blocks validated, {corrupt} corrupted blocks, seed {seed}", flush=True)
+print(f"fuzz {'ok' if not ratio_fail else 'RATIO FAILURES ' + str(ratio_fail)}: {rounds} rounds, {blocks} blocks validated, {corrupt} corrupted blocks, {frames_bad} damaged frames, seed {seed}", flush=True)
