@@ -218,8 +218,9 @@ inline cudaError_t v6_launch_decompress(int team, const u8* in, const u64* in_of
 {
     const int d = v6_depth();
     if (team == 4) {
-        if (d == 3) return v6_launch_t<4, 3>(in, in_off, csz, out_off, usz, out, status, bad, n, ticket, sm_count, st);
-        if (d == 4) return v6_launch_t<4, 4>(in, in_off, csz, out_off, usz, out, status, bad, n, ticket, sm_count, st);
+        // depth <= 3 on 4-lane teams: a ring segment (64 bytes here) is requested two segments ahead and must have landed
+        // >= 3 iterations later, which wait_group 3 would not guarantee
+        if (d >= 3) return v6_launch_t<4, 3>(in, in_off, csz, out_off, usz, out, status, bad, n, ticket, sm_count, st);
         return v6_launch_t<4, 2>(in, in_off, csz, out_off, usz, out, status, bad, n, ticket, sm_count, st);
     }
     if (team == 16) {
