@@ -28,10 +28,15 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, u32
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
 
-struct V5Team { const u8* src; u32 clen, n, chunk, raw; };   // cold per-team state (aligned coordinates, see below)
+struct V5Team { const u8* src; u32 clen, n, chunk, raw, cap; };   // cold per-team state (aligned coordinates, see below)
 struct V5Params {
     const u8* in; const u64* in_off; const u64* csz; const u64* out_off; const u64* usz; u8* out;
     u32* status; u32* bad_chunks; u32* ticket; u32 n_chunks;
+    // 0: every chunk's end-of-block rules are checked against its own size (lzbench hands the exact size to the decoder);
+    // else: against this capacity, as LZ4F_decompress does, which decodes every block into a buffer of the frame's block
+    // size (lz4/lz4frame.c:1384-1830) -- a block that ends closer than 12 / 5 bytes behind its last match is then accepted,
+    // and so it must be here (found by scripts/fuzz_gpu.py on a damaged frame).  The decoded size is checked either way.
+    u32 cap_all;
 };
 // loop-carried state of one lane, handed to the cold function through local memory
 struct V5State { u8* dst; u32 ip, op, tok, pm_len, op_safe, ip_safe, rem; bool busy, exhausted, fastable; u32 lrem; };
@@ -65,7 +70,7 @@ __device__ __noinline__ bool v5_cold(V5State& S, const bool f, const V5Params& P
     bool restart = false;                          // the read position moved outside the common path: ring upkeep, reload tok
     bool fresh = false;                            // new chunk
     const u8* src = ts.src;
-    u32 clen = ts.clen, n = ts.n;
+    u32 clen = ts.clen, n = ts.n, capv = ts.cap;
     // stream bytes below `landed` are in the ring (segments seg0 and seg0 + 1 are complete, seg0 + 2 may be in flight)
     const u32 seg0 = ip / SEG;
     const u32 landed = fastable ? (seg0 + 2) * SEG : 0u;
@@ -96,7 +101,7 @@ __device__ __noinline__ bool v5_cold(V5State& S, const bool f, const V5Params& P
                 }
                 const u64 cpy = op + len;
                 if (err) finished = true;
-                else if (cpy + MFLIMIT > n || ip + len + (2 + 1 + LASTLITERALS) > clen) {     // last sequence
+                else if (cpy + MFLIMIT > capv || ip + len + (2 + 1 + LASTLITERALS) > clen) {  // last sequence
                     if (ip + len != clen || cpy > n) err = ST_LAST_LITERALS;
                     else {
                         const u32 LL = (u32)len;
@@ -122,7 +127,7 @@ __device__ __noinline__ bool v5_cold(V5State& S, const bool f, const V5Params& P
                     }
                     ml64 += MINMATCH;
                     if (!err && (off == 0 || off > op)) err = ST_OFFSET;
-                    if (!err && op + ml64 + LASTLITERALS > n) err = ST_MATCH_END;
+                    if (!err && (op + ml64 + LASTLITERALS > capv || op + ml64 > n)) err = ST_MATCH_END;
                     if (err) { finished = true; wl_len = 0; }
                     else {
                         const u32 ml = (u32)ml64;
@@ -180,12 +185,13 @@ __device__ __noinline__ bool v5_cold(V5State& S, const bool f, const V5Params& P
             op = 0; busy = true; S.pm_len = 0; S.rem = 0; S.lrem = 0;
             const bool raw = clen == n;
             fastable = !raw && n >= 32 && clen >= 24;
-            S.op_safe = fastable ? n - MFLIMIT : 0;        // match end + MFLIMIT <= n (non-last sequence, lz4/lz4.c:1990,:2139)
+            capv = P.cap_all > n ? P.cap_all : n;
+            S.op_safe = fastable ? capv - MFLIMIT : 0;     // match end + MFLIMIT <= capacity (non-last sequence, lz4/lz4.c:1990,:2139)
             ip = (u32)(reinterpret_cast<uintptr_t>(src) & 15u);
             src -= ip; clen += ip;                         // aligned coordinates
             S.ip_safe = fastable ? clen - 21 : 0;          // next token + 17 bytes (at ip + L + 3 or 4) stay inside the chunk
             __syncwarp(tmask);                             // the team's earlier reads of ts are done
-            if (j == 0) { ts.src = src; ts.clen = clen; ts.n = n; ts.chunk = c; ts.raw = raw; }
+            if (j == 0) { ts.src = src; ts.clen = clen; ts.n = n; ts.chunk = c; ts.raw = raw; ts.cap = capv; }
             restart = true; fresh = true;
         }
     }
@@ -367,7 +373,7 @@ decompress_v5_kernel(const __grid_constant__ V5Params P)
 
 template <u32 T>
 inline cudaError_t v5_launch_t(const u8* in, const u64* in_off, const u64* csz, const u64* out_off, const u64* usz,
-                               u8* out, u32* status, u32* bad, u32 n, u32* ticket, int sm_count, cudaStream_t st)
+                               u8* out, u32* status, u32* bad, u32 n, u32* ticket, int sm_count, cudaStream_t st, u32 cap_all)
 {
     const u32 teams_per_block = V2_BLOCK / T;
     int per_sm = 0;
@@ -379,18 +385,18 @@ inline cudaError_t v5_launch_t(const u8* in, const u64* in_off, const u64* csz, 
     if (grid > need) grid = need;
     e = cudaMemsetAsync(ticket, 0, sizeof(u32), st);
     if (e != cudaSuccess) return e;
-    const V5Params P{ in, in_off, csz, out_off, usz, out, status, bad, ticket, n };
+    const V5Params P{ in, in_off, csz, out_off, usz, out, status, bad, ticket, n, cap_all };
     decompress_v5_kernel<T><<<grid, V2_BLOCK, 0, st>>>(P);
     return cudaGetLastError();
 }
 
 inline cudaError_t v5_launch_decompress(int team, const u8* in, const u64* in_off, const u64* csz, const u64* out_off,
                                         const u64* usz, u8* out, u32* status, u32* bad, u32 n, u32* ticket,
-                                        int sm_count, cudaStream_t st)
+                                        int sm_count, cudaStream_t st, u32 cap_all = 0)
 {
-    if (team == 16) return v5_launch_t<16>(in, in_off, csz, out_off, usz, out, status, bad, n, ticket, sm_count, st);
-    if (team == 4) return v5_launch_t<4>(in, in_off, csz, out_off, usz, out, status, bad, n, ticket, sm_count, st);
-    return v5_launch_t<8>(in, in_off, csz, out_off, usz, out, status, bad, n, ticket, sm_count, st);
+    if (team == 16) return v5_launch_t<16>(in, in_off, csz, out_off, usz, out, status, bad, n, ticket, sm_count, st, cap_all);
+    if (team == 4) return v5_launch_t<4>(in, in_off, csz, out_off, usz, out, status, bad, n, ticket, sm_count, st, cap_all);
+    return v5_launch_t<8>(in, in_off, csz, out_off, usz, out, status, bad, n, ticket, sm_count, st, cap_all);
 }
 
 }  // namespace lz4b200

@@ -304,7 +304,7 @@ int compress_slice(lz4b200_ctx* c, const u8* d_in, const u64* d_usz, size_t n, s
 
 int decompress_slice(lz4b200_ctx* c, const u8* d_in, const u64* d_csz, const u64* d_usz, size_t n, size_t max_chunk,
                      u8* d_out, u32* d_bad, const Scratch& s_in, cudaStream_t st, int team = 0,
-                     const u64* given_coff = nullptr)
+                     const u64* given_coff = nullptr, u32 cap_all = 0)
 {
     // given_coff: the chunks are not contiguous in d_in (frame blocks have a size word between them); the caller has
     // filled their positions and s.uoff (absolute output offsets) itself.
@@ -333,7 +333,7 @@ int decompress_slice(lz4b200_ctx* c, const u8* d_in, const u64* d_csz, const u64
         c->launches += 1;
     } else if (c->kernel_gen == 5 && team != 32) {
         CU(v5_launch_decompress(team, d_in, s.coff, d_csz, s.uoff, d_usz, d_out, s.status, d_bad, (u32)n,
-                                s.ticket, c->sm_count, st));
+                                s.ticket, c->sm_count, st, cap_all));
         c->launches += 1;
     } else if (c->kernel_gen == 4 && team != 32) {
         CU(v4_launch_decompress(team, d_in, s.coff, d_csz, s.uoff, d_usz, d_out, s.status, d_bad, (u32)n,
@@ -950,7 +950,7 @@ int64_t lz4b200_frame_decompress(lz4b200_ctx* c, const char* in, size_t in_size,
         frame_guard_kernel<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(usz_k, csz_k, (u32)m, running + k, (u64)limit);
         c->launches += 2;
         int rc = decompress_slice(c, (const u8*)c->d_packed.p, csz_k, usz_k, m, fi.block_max, (u8*)c->d_plain.p, d_bad,
-                                  sk, st, 0, d_pos + f);
+                                  sk, st, 0, d_pos + f, (u32)fi.block_max);
         if (rc) { cudaDeviceSynchronize(); return rc; }
         CU(cudaEventRecord(c->ev_done[k], st));
     }

@@ -13,6 +13,7 @@
 #include <stdint.h>
 #include <stddef.h>
 #include <string.h>
+#include <stdlib.h>
 #include "lz4_oracle.h"
 
 static inline uint32_t rotl32(uint32_t x, int r) { return (x << r) | (x >> (32 - r)); }
@@ -103,10 +104,21 @@ size_t oracle_lz4f_decompress(const uint8_t* src, size_t n, uint8_t* dst, size_t
             if (op + sz > cap) return (size_t)-1;
             memcpy(dst + op, src + ip, sz); op += sz;
         } else {
-            const size_t room = cap - op < bmax ? cap - op : bmax;
-            int r = oracle_lz4_decompress_safe(src + ip, (int)sz, dst + op, (int)room);
-            if (r < 0) return (size_t)-1;
-            op += (size_t)r;
+            /* lz4/lz4frame.c:1654-1712: a block is always decoded with the frame's block size as capacity (into the
+             * caller's buffer when that much room is left, else into the context's own buffer and copied) */
+            if (cap - op >= bmax) {
+                int r = oracle_lz4_decompress_safe(src + ip, (int)sz, dst + op, (int)bmax);
+                if (r < 0) return (size_t)-1;
+                op += (size_t)r;
+            } else {
+                uint8_t* tmp = (uint8_t*)malloc(bmax);
+                if (!tmp) return (size_t)-1;
+                int r = oracle_lz4_decompress_safe(src + ip, (int)sz, tmp, (int)bmax);
+                if (r < 0 || (size_t)r > cap - op) { free(tmp); return (size_t)-1; }
+                memcpy(dst + op, tmp, (size_t)r);
+                free(tmp);
+                op += (size_t)r;
+            }
         }
         ip += sz + (bck ? 4 : 0);
     }

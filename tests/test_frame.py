@@ -73,3 +73,34 @@ def test_damaged_frames_rejected_by_both():
     for g in cases:
         assert O.ref_frame_decompress(g, len(d) + 16)[0] == O.BAD
         assert O.oracle_frame_decompress(g, len(d) + 16)[0] == O.BAD
+
+
+@needs_ref
+def test_random_damage_same_verdict_as_reference():
+    """The frame oracle must agree with LZ4F_decompress on damaged frames too (accept / reject, and the bytes when both
+    accept): it is what the GPU frame decoder is fuzzed against (scripts/fuzz_gpu.py)."""
+    rng = np.random.default_rng(77)
+    trials = stricter = 0
+    for kind, n, bid in (("mixed", 300000, 4), ("mixed", 70000, 4), ("repeat", 200000, 5), ("mixed", 1 << 20, 6)):
+        d = L.corpus(kind, n, seed=5)
+        for cck, csz in ((0, 0), (1, 1)):
+            f = O.oracle_frame_compress(d, bid, cck, csz)
+            for _ in range(400):
+                g = f.copy()
+                for _ in range(int(rng.integers(1, 4))):
+                    g[int(rng.integers(0, len(g)))] ^= 1 << int(rng.integers(0, 8))
+                if rng.random() < 0.15:
+                    g = g[:int(rng.integers(1, len(g)))].copy()
+                ro, oo = O.oracle_frame_decompress(g, n + 8)
+                rr, orf = O.ref_frame_decompress(g, n + 8)
+                trials += 1
+                if rr == O.BAD:
+                    assert ro == O.BAD, (kind, n, bid, cck, "oracle accepts what the reference rejects")
+                elif ro != O.BAD:
+                    assert ro == rr and np.array_equal(oo, orf)
+                else:
+                    # the one documented deviation: a match offset of 0 (here: 16 with its only bit flipped) is rejected by
+                    # the oracle and the product, while the reference copies indeterminate bytes (DESIGN.md section 2)
+                    assert not np.array_equal(orf, d)
+                    stricter += 1
+    assert stricter <= 0.02 * trials
