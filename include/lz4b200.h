@@ -103,15 +103,20 @@ int lz4b200_kernel_times_ms(lz4b200_ctx* ctx, float* out_ms, int max_n);
  * copies 16 counters to out16 and clears them. */
 int lz4b200_debug_prof(lz4b200_ctx* ctx, uint64_t* out16);
 
-/* Tunable: which decode kernel generation to run: "kernels" = "v0" (warp per chunk), "v1"
- * (one CTA per chunk, TMA-staged shared-memory tile, speculative parallel parse), "v2"
- * (sub-warp teams), "v3" (v2 + every output byte owned by a fixed lane, match store pipelined one sequence behind
- * its load, no barriers on the fast path), "v4" (v3 with a warp-uniform, predicated fast path; default);
- * "team" = "8"/"16" lanes per chunk (v2 also "4"/"32").  "compress" = "v0"/"v1" picks the compressor generation; "slices" = number of H2D/kernel/D2H
- * pipeline slices of the host entry points (0 = automatic); "host_register" = "1" page-locks caller
- * buffers on first sight (what the lzbench wrappers turn on).  "accel" = LZ4_compress_fast's acceleration (lz4/lz4.c:1352-1375; the lz4fast levels of lzbench, _lzbench/compressors.cpp:348-356):
- * 1 default, 2-3 probe every 2nd position, >= 4 every 4th.  Also "timing" = "0"/"1" (see above).  Returns 0, or -1 for an unknown key or value.
- * Default kernels: the fastest verified generation. */
+/* Options (key, value as strings).  Returns 0, or -1 for an unknown key or value.
+ *   "kernels"  decode generation: "v0" warp per chunk; "v1" one CTA per chunk, TMA-staged tile, speculative parallel parse;
+ *              "v2" sub-warp teams; "v3" + every output byte owned by a fixed lane, match store pipelined behind its load;
+ *              "v4" + warp-uniform predicated fast path; "v5" (default) + compressed stream through a cp.async shared-memory
+ *              ring, long literal runs on the fast path, slow path out of line; "v6" experiment: v5 with the pending match
+ *              bytes staged by cp.async ("depth" = "2".."4" iterations in flight).  Also sets the matching compressor.
+ *   "team"     lanes per chunk for the team decoders: "4" / "8" / "16" / "32", "0" = by batch size (default)
+ *   "compress" compressor generation: "v0" warp per chunk, "v1" one CTA per chunk, "v2" (default) two warp groups per CTA
+ *   "accel"    LZ4_compress_fast's acceleration (lz4/lz4.c:1352-1375; the lz4fast levels of lzbench,
+ *              _lzbench/compressors.cpp:348-356): 1 default, 2-3 probe every 2nd position, >= 4 every 4th
+ *   "slices"   pipeline slices of the host entry points (0 = automatic); "ramp" = "0"/"1" small first slices when
+ *              decompressing (default 1); "h2d" = "own"/"shared" stream for the inbound copies (default own)
+ *   "host_register" = "1" page-locks caller buffers on first sight (what the lzbench wrappers turn on)
+ *   "timing" = "0"/"1" (see lz4b200_kernel_times_ms), "prof" = "0"/"1" (see lz4b200_debug_prof), "c1mode" (match-finder variant) */
 int lz4b200_set_option(lz4b200_ctx* ctx, const char* key, const char* value);
 
 /* ---- lzbench plugin-signature wrappers (drop-in comp_desc[] row "lz4_b200") -------------- */
