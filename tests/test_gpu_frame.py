@@ -108,3 +108,25 @@ def test_frame_256mib_round_trip(gpu_ctx):
     for name, dec in decoders():
         r, out = dec(f, n)
         assert r == n and np.array_equal(out, d), name
+
+
+def test_block_rules_are_checked_against_the_frame_block_size(gpu_ctx):
+    """LZ4F_decompress decodes every block into a buffer of the frame's block size, so the end-of-block rules are
+    relative to that capacity (lz4/lz4frame.c:1654-1712): this block ends 4 bytes behind its last match, which
+    LZ4_decompress_safe rejects when told the exact size (27) and accepts with room to spare.  Frames must follow the
+    frame decoder, chunks the block decoder."""
+    blk = np.frombuffer(bytes([0x4F]) + b"abcd" + bytes([4, 0, 0, 0x40]) + b"wxyz", dtype=np.uint8)
+    want = np.frombuffer(b"abcd" + (b"abcd" * 5)[:19] + b"wxyz", dtype=np.uint8)
+    frame = np.concatenate([np.frombuffer(b"\x04\x22\x4d\x18\x60\x40\x82", dtype=np.uint8),
+                            np.frombuffer(np.uint32(len(blk)).tobytes(), dtype=np.uint8), blk, np.zeros(4, np.uint8)])
+    for name, dec in decoders():
+        r, out = dec(frame, 100)
+        assert r == len(want) and np.array_equal(out, want), name
+    r, out = gpu_ctx.frame_decompress(frame, 100)
+    assert r == len(want) and np.array_equal(out, want), L.last_error()
+    # the same block as an lzbench chunk of exactly 27 bytes is malformed for every block decoder
+    assert O.oracle_decompress(blk, 27)[0] < 0
+    if O.ref is not None:
+        assert O.ref_decompress_safe(blk, 27)[0] < 0
+    _, r = gpu_ctx.decompress_batch(blk, np.array([len(blk)], dtype=np.uint64), np.array([27], dtype=np.uint64))
+    assert r < 0
