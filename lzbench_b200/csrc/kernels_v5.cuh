@@ -37,6 +37,9 @@ struct V5Params {
     // size (lz4/lz4frame.c:1384-1830) -- a block that ends closer than 12 / 5 bytes behind its last match is then accepted,
     // and so it must be here (found by scripts/fuzz_gpu.py on a damaged frame).  The decoded size is checked either way.
     u32 cap_all;
+    // optional work list (kernels_v7.cuh leaves the chunks that are mostly long copies to this kernel): tickets index
+    // list[0 .. *list_count) instead of the chunks themselves
+    const u32* list; const u32* list_count;
 };
 // loop-carried state of one lane, handed to the cold function through local memory
 struct V5State { u8* dst; u32 ip, op, tok, pm_len, op_safe, ip_safe, rem; bool busy, exhausted, fastable; u32 lrem; };
@@ -178,8 +181,9 @@ __device__ __noinline__ bool v5_cold(V5State& S, const bool f, const V5Params& P
         u32 c = 0;
         if (j == 0) c = atomicAdd(P.ticket, 1u);
         c = __shfl_sync(tmask, c, tbase);
-        if (c >= P.n_chunks) exhausted = true;
+        if (c >= (P.list ? *P.list_count : P.n_chunks)) exhausted = true;
         else {
+            if (P.list) c = P.list[c];
             src = P.in + P.in_off[c]; clen = (u32)P.csz[c];
             dst = P.out + P.out_off[c]; n = (u32)P.usz[c];
             op = 0; busy = true; S.pm_len = 0; S.rem = 0; S.lrem = 0;
@@ -373,7 +377,8 @@ decompress_v5_kernel(const __grid_constant__ V5Params P)
 
 template <u32 T>
 inline cudaError_t v5_launch_t(const u8* in, const u64* in_off, const u64* csz, const u64* out_off, const u64* usz,
-                               u8* out, u32* status, u32* bad, u32 n, u32* ticket, int sm_count, cudaStream_t st, u32 cap_all)
+                               u8* out, u32* status, u32* bad, u32 n, u32* ticket, int sm_count, cudaStream_t st, u32 cap_all,
+                               const u32* list, const u32* list_count)
 {
     const u32 teams_per_block = V2_BLOCK / T;
     int per_sm = 0;
@@ -385,18 +390,19 @@ inline cudaError_t v5_launch_t(const u8* in, const u64* in_off, const u64* csz, 
     if (grid > need) grid = need;
     e = cudaMemsetAsync(ticket, 0, sizeof(u32), st);
     if (e != cudaSuccess) return e;
-    const V5Params P{ in, in_off, csz, out_off, usz, out, status, bad, ticket, n, cap_all };
+    const V5Params P{ in, in_off, csz, out_off, usz, out, status, bad, ticket, n, cap_all, list, list_count };
     decompress_v5_kernel<T><<<grid, V2_BLOCK, 0, st>>>(P);
     return cudaGetLastError();
 }
 
 inline cudaError_t v5_launch_decompress(int team, const u8* in, const u64* in_off, const u64* csz, const u64* out_off,
                                         const u64* usz, u8* out, u32* status, u32* bad, u32 n, u32* ticket,
-                                        int sm_count, cudaStream_t st, u32 cap_all = 0)
+                                        int sm_count, cudaStream_t st, u32 cap_all = 0,
+                                        const u32* list = nullptr, const u32* list_count = nullptr)
 {
-    if (team == 16) return v5_launch_t<16>(in, in_off, csz, out_off, usz, out, status, bad, n, ticket, sm_count, st, cap_all);
-    if (team == 4) return v5_launch_t<4>(in, in_off, csz, out_off, usz, out, status, bad, n, ticket, sm_count, st, cap_all);
-    return v5_launch_t<8>(in, in_off, csz, out_off, usz, out, status, bad, n, ticket, sm_count, st, cap_all);
+    if (team == 16) return v5_launch_t<16>(in, in_off, csz, out_off, usz, out, status, bad, n, ticket, sm_count, st, cap_all, list, list_count);
+    if (team == 4) return v5_launch_t<4>(in, in_off, csz, out_off, usz, out, status, bad, n, ticket, sm_count, st, cap_all, list, list_count);
+    return v5_launch_t<8>(in, in_off, csz, out_off, usz, out, status, bad, n, ticket, sm_count, st, cap_all, list, list_count);
 }
 
 }  // namespace lz4b200

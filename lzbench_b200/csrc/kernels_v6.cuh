@@ -205,7 +205,7 @@ inline cudaError_t v6_launch_t(const u8* in, const u64* in_off, const u64* csz, 
     if (grid > need) grid = need;
     e = cudaMemsetAsync(ticket, 0, sizeof(u32), st);
     if (e != cudaSuccess) return e;
-    const V5Params P{ in, in_off, csz, out_off, usz, out, status, bad, ticket, n, 0u };
+    const V5Params P{ in, in_off, csz, out_off, usz, out, status, bad, ticket, n, 0u, nullptr, nullptr };
     decompress_v6_kernel<T, DEPTH><<<grid, V2_BLOCK, 0, st>>>(P);
     return cudaGetLastError();
 }

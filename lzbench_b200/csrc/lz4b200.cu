@@ -14,6 +14,7 @@
 #include "kernels_v4.cuh"
 #include "kernels_v5.cuh"
 #include "kernels_v6.cuh"
+#include "kernels_v7.cuh"
 #include "kernels_c1.cuh"
 #include "kernels_c2.cuh"
 #include "segmented.cuh"
@@ -85,7 +86,7 @@ struct PinBuf {
 struct lz4b200_ctx {
     int device = 0;
     int sm_count = 148;
-    int kernel_gen = 5;                 // decode: 0 warp per chunk, 1 CTA tile (TMA), 2 sub-warp teams, 3 + mapped lanes / pipelined match, 4 + warp-uniform fast path, 5 + compressed stream through a cp.async ring, long literal runs on the common path (default), 6 = 5 with cp.async-staged deep match pipeline (experiment)
+    int kernel_gen = 7;                 // decode: 7 = sequence table + one lane per sequence (kernels_v7.cuh; default for chunks <= 64 KiB, v5 otherwise and for the chunks v7 leaves to it); 0 warp per chunk, 1 CTA tile (TMA), 2 sub-warp teams, 3 + mapped lanes / pipelined match, 4 + warp-uniform fast path, 5 + compressed stream through a cp.async ring, long literal runs on the common path (default), 6 = 5 with cp.async-staged deep match pipeline (experiment)
     int compress_gen = 2;               // compress: 0 warp per chunk, 1 CTA per chunk (parallel match finder + speculative parse), 2 = 1 with the phases on two warp groups (default)
     int accel = 1;                      // compress: LZ4_compress_fast's acceleration (1 = lz4 default; lz4fast levels), probe grid 1/2/4/8
     int team = 0;                       // lanes per chunk for the team decoders: 8 / 16 / 32, 0 = by batch size
@@ -118,6 +119,10 @@ struct lz4b200_ctx {
     bool prof_on = false;
     DevBuf stage;                       // compress: n_chunks slots of slot_stride bytes (or one slot per 64 KiB segment)
     DevBuf seg64, seg32;                // segmented compress (segmented.cuh): u64 / u32 job arrays
+    DevBuf v7_table, v7_u32;            // v7 decode: sequence table (u64 entries) and nseq / route / team list (u32[3][n_chunks])
+    size_t v7_chunks = 0;               // chunk count the u32 arrays are laid out for (current call)
+    size_t v7_table_chunks = 0;         // chunks the table has room for (current call): all of a host call's, one sub-batch of a device call's
+    size_t v7_per_chunk = 0;            // table entries reserved per chunk (current call)
     // buffers behind the host entry points
     DevBuf d_plain, d_packed;
     PinBuf h_sizes;                     // u64[2*n_chunks + MAX_SLICES + 2]
@@ -135,6 +140,7 @@ constexpr size_t SC_FUNSUP = 24;        // u32  frame container: blocks the size
 constexpr size_t SC_FCK = 28;           // u32  frame container: block checksum mismatches
 constexpr size_t SC_TICKETS = 256;      // u32[MAX_SLICES] work tickets, one per slice
 constexpr size_t SC_NJOBS = 1024;        // u64[MAX_SLICES] job counts of the segmented compressor, one per slice
+constexpr size_t SC_TEAMCOUNT = 2048;    // u32[MAX_SLICES] v7: chunks left to the team decoder, one counter per slice
 constexpr size_t SC_RUNNING = 4096;     // u64[MAX_SLICES] running compressed totals after each slice
 constexpr size_t SC_BYTES = 8192;
 
@@ -142,6 +148,7 @@ constexpr size_t SC_BYTES = 8192;
 struct Scratch {
     u64* uoff; u64* coff; u32* status; u8* stage; u32* ticket;
     u64* fsz;                          // frame mode only
+    u64* v7_table; u64 v7_cap; u32 *v7_nseq, *v7_route, *v7_list, *v7_count;   // kernels_v7.cuh (null: not available)
     size_t first_chunk;                // slices of one call own disjoint regions of the per-chunk / per-job arrays
 };
 
@@ -193,6 +200,19 @@ int ensure_scratch(lz4b200_ctx* c, size_t n, size_t stage_bytes)
     return 0;
 }
 
+// v7 decode scratch: u32 arrays for n chunks, table room for table_chunks chunks of at most max_chunk bytes.  Failing to
+// get the memory is not an error: the slice then runs on the team decoder.
+constexpr size_t V7_SUB = 16384;            // chunks per sub-batch of a device-resident call (bounds the table: 2 x their bytes)
+void ensure_v7(lz4b200_ctx* c, size_t n, size_t table_chunks, size_t max_chunk)
+{
+    c->v7_chunks = c->v7_table_chunks = 0;
+    if (c->kernel_gen != 7 || max_chunk > V7_MAX_CHUNK || n == 0) return;
+    c->v7_per_chunk = (size_t)v7_entries_for(max_chunk, 1);
+    if (c->v7_u32.ensure(3 * n * sizeof(u32)) != cudaSuccess ||
+        c->v7_table.ensure(table_chunks * c->v7_per_chunk * sizeof(u64)) != cudaSuccess) { cudaGetLastError(); return; }
+    c->v7_chunks = n; c->v7_table_chunks = table_chunks;
+}
+
 Scratch scratch_at(lz4b200_ctx* c, size_t first_chunk, size_t stride, int slice)
 {
     Scratch s;
@@ -202,6 +222,17 @@ Scratch scratch_at(lz4b200_ctx* c, size_t first_chunk, size_t stride, int slice)
     s.stage = c->stage.p ? (u8*)c->stage.p + first_chunk * stride : nullptr;   // `stride` = staging bytes per chunk
     s.ticket = (u32*)((u8*)c->scalars.p + SC_TICKETS) + slice;
     s.fsz = c->fsz.p ? (u64*)c->fsz.p + first_chunk : nullptr;
+    s.v7_table = nullptr; s.v7_cap = 0; s.v7_nseq = s.v7_route = s.v7_list = s.v7_count = nullptr;
+    if (c->v7_table.p && c->v7_chunks && first_chunk < c->v7_chunks) {
+        // every slice owns the table region of its chunks (slices of one host call run concurrently)
+        if (first_chunk < c->v7_table_chunks) {
+            s.v7_table = (u64*)c->v7_table.p + first_chunk * c->v7_per_chunk;
+            s.v7_cap = (c->v7_table_chunks - first_chunk) * c->v7_per_chunk;
+        }
+        u32* b = (u32*)c->v7_u32.p;
+        s.v7_nseq = b + first_chunk; s.v7_route = b + c->v7_chunks + first_chunk; s.v7_list = b + 2 * c->v7_chunks + first_chunk;
+        s.v7_count = (u32*)((u8*)c->scalars.p + SC_TEAMCOUNT) + slice;
+    }
     s.first_chunk = first_chunk;
     return s;
 }
@@ -323,11 +354,27 @@ int decompress_slice(lz4b200_ctx* c, const u8* d_in, const u64* d_csz, const u64
         // measured (scripts/team_probe.py, gpu_probe.py): 1024 chunks take 2.0 ms on 16 lanes, 2.6 on 8, 3.7 on a warp (v2);
         // 4-lane teams (8 chunks per warp) only pay once there are enough chunks to fill the machine with them
         // (262 144 chunks of 4 KiB: 357 vs 301 GB/s; 65 536 of 16 KiB: 250 vs 294)
-        if (c->kernel_gen == 5) team = n * 2 <= (size_t)c->sm_count * 32 ? 16 : (n >= (size_t)c->sm_count * 7 * 32 * 4 ? 4 : 8);
+        if (c->kernel_gen == 5 || c->kernel_gen == 7) team = n * 2 <= (size_t)c->sm_count * 32 ? 16 : (n >= (size_t)c->sm_count * 7 * 32 * 4 ? 4 : 8);
         else if (c->kernel_gen >= 5) team = n * 2 <= (size_t)c->sm_count * 32 ? 16 : 8;
         else team = n * 4 <= (size_t)c->sm_count * 32 ? 32 : (n * 2 <= (size_t)c->sm_count * 32 ? 16 : 8);
     }
-    if (c->kernel_gen == 6 && team != 32) {
+    if (c->kernel_gen == 7 && s.v7_table && max_chunk <= V7_MAX_CHUNK) {
+        // sequence table, lane-per-sequence decoder, then the team decoder for the chunks left on the list
+        for (size_t b = 0; b < n; b += V7_SUB) {
+            const size_t m = std::min(V7_SUB, n - b);
+            V7Params P{ d_in, s.coff + b, d_csz + b, s.uoff + b, d_usz + b, d_out, s.status + b, d_bad, s.ticket, (u32)m, cap_all,
+                        s.v7_table, s.v7_cap, s.v7_nseq + b, s.v7_route + b, s.v7_list + b, s.v7_count };
+            CU(v7_launch_parse(P, st));
+            CU(v7_launch_decompress(P, c->sm_count, st));
+            CU(v5_launch_decompress(team == 32 ? 16 : team, d_in, s.coff + b, d_csz + b, s.uoff + b, d_usz + b, d_out,
+                                    s.status + b, d_bad, (u32)m, s.ticket, c->sm_count, st, cap_all, s.v7_list + b, s.v7_count));
+            c->launches += 3;
+        }
+    } else if (c->kernel_gen >= 7) {
+        CU(v5_launch_decompress(team == 32 ? 16 : team, d_in, s.coff, d_csz, s.uoff, d_usz, d_out, s.status, d_bad, (u32)n,
+                                s.ticket, c->sm_count, st, cap_all));
+        c->launches += 1;
+    } else if (c->kernel_gen == 6 && team != 32) {
         CU(v6_launch_decompress(team, d_in, s.coff, d_csz, s.uoff, d_usz, d_out, s.status, d_bad, (u32)n,
                                 s.ticket, c->sm_count, st));
         c->launches += 1;
@@ -481,6 +528,7 @@ int lz4b200_create(int device, size_t max_total_bytes, size_t max_chunk_bytes, l
     if (gen && !strcmp(gen, "v4")) c->kernel_gen = 4;
     if (gen && !strcmp(gen, "v5")) c->kernel_gen = 5;
     if (gen && !strcmp(gen, "v6")) c->kernel_gen = 6;
+    if (gen && !strcmp(gen, "v7")) c->kernel_gen = 7;
     for (int i = 0; i < lz4b200_ctx::NS; i++) {
         cudaError_t e = cudaStreamCreateWithFlags(&c->streams[i], cudaStreamNonBlocking);
         if (e != cudaSuccess) { lz4b200_destroy(c); return fail(-2, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
@@ -528,7 +576,7 @@ void lz4b200_destroy(lz4b200_ctx* c)
     c->usz.release(); c->csz.release(); c->uoff.release(); c->coff.release();
     c->scalars.release(); c->status.release(); c->stage.release(); c->seg64.release(); c->seg32.release();
     c->d_plain.release(); c->d_packed.release(); c->h_sizes.release(); c->prof.release();
-    c->fsz.release(); c->fhdr.release();
+    c->fsz.release(); c->fhdr.release(); c->v7_table.release(); c->v7_u32.release();
     if (c->h_mirror) cudaFreeHost(c->h_mirror);
     for (int i = 0; i < lz4b200_ctx::MAX_TIMED; i++) if (c->ev0[i]) { cudaEventDestroy(c->ev0[i]); cudaEventDestroy(c->ev1[i]); }
     delete c;
@@ -547,6 +595,7 @@ int lz4b200_set_option(lz4b200_ctx* c, const char* key, const char* value)
         if (!strcmp(value, "v4")) { c->kernel_gen = 4; c->compress_gen = 2; return 0; }
         if (!strcmp(value, "v5")) { c->kernel_gen = 5; c->compress_gen = 2; return 0; }
         if (!strcmp(value, "v6")) { c->kernel_gen = 6; c->compress_gen = 2; return 0; }
+        if (!strcmp(value, "v7") || !strcmp(value, "default")) { c->kernel_gen = 7; c->compress_gen = 2; return 0; }
     }
     if (!strcmp(key, "compress")) {
         if (!strcmp(value, "v0")) { c->compress_gen = 0; return 0; }
@@ -629,6 +678,7 @@ int lz4b200_decompress_device(lz4b200_ctx* c, const void* d_in, const uint64_t* 
     cudaStream_t st = (cudaStream_t)stream;
     CU(cudaSetDevice(c->device));
     if (int rc = ensure_scratch(c, n ? n : 1, 0)) return rc;
+    ensure_v7(c, n, std::min(n, V7_SUB), max_chunk);
     u32* bad = d_bad_chunks ? d_bad_chunks : (u32*)((u8*)c->scalars.p + SC_BAD);
     CU(cudaMemsetAsync(bad, 0, sizeof(u32), st));
     if (n == 0) return 0;
@@ -749,6 +799,7 @@ int64_t lz4b200_decompress_batch(lz4b200_ctx* c, const char* in, const size_t* c
     CU(c->d_plain.ensure(total + 16));
     CU(c->d_packed.ensure(ctotal + 16));
     if (int rc = ensure_scratch(c, n, 0)) return rc;
+    ensure_v7(c, n, n, max_chunk);
     size_t first[lz4b200_ctx::MAX_SLICES + 1];
     const int K = plan_slices(c, chunk_sizes, n, total, true, first);
     if (int rc = ensure_events(c, K)) return rc;
@@ -913,6 +964,7 @@ int64_t lz4b200_frame_decompress(lz4b200_ctx* c, const char* in, size_t in_size,
     CU(c->d_packed.ensure(frame_bytes + 16));
     CU(c->d_plain.ensure(limit + 16));
     if (int rc = ensure_scratch(c, n, 0)) return rc;
+    ensure_v7(c, n, n, fi.block_max);
     size_t first[lz4b200_ctx::MAX_SLICES + 1];
     const int K = plan_slices(c, weight.data(), n, frame_bytes, true, first);
     if (int rc = ensure_events(c, K)) return rc;

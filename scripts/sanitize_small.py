@@ -13,7 +13,7 @@ n = int(cs.sum())
 for kind in ("mixed", "random", "zero"):
     data = L.corpus(kind, n, seed=2)
     p_ref, c_ref = O.oracle_chunked_compress(data, cs)
-    for gen in ("v0", "v1", "v2", "v3", "v4", "v5", "v6"):
+    for gen in ("v0", "v1", "v2", "v3", "v4", "v5", "v6", "v7"):
         ctx.set_option("kernels", gen)
         packed, compr, total = ctx.compress_batch(data, cs)
         out, r = ctx.decompress_batch(packed[:total], compr, cs)
@@ -23,7 +23,7 @@ for kind in ("mixed", "random", "zero"):
     # corrupted blocks must be rejected without touching memory out of bounds
     bad = p_ref.copy()
     for i in rng.integers(0, len(bad), 200): bad[int(i)] = int(rng.integers(0, 256))
-    for gen in ("v0", "v1", "v2", "v3", "v4", "v5", "v6"):
+    for gen in ("v0", "v1", "v2", "v3", "v4", "v5", "v6", "v7"):
         ctx.set_option("kernels", gen)
         ctx.decompress_batch(bad, c_ref, cs)
 print("sanitize_small ok")

@@ -21,6 +21,14 @@ RATIO_TOLERANCE = 1.03
 CORPORA = [("mixed", 1), ("random", 4), ("repeat", 5), ("zero", 5)]
 
 
+@pytest.fixture(autouse=True)
+def _default_kernels(gpu_ctx):
+    """The context is shared by the session: every test starts from the default kernel selection."""
+    gpu_ctx.set_option("kernels", "default")
+    gpu_ctx.set_option("team", "0")
+    yield
+
+
 def check_gpu_blocks_with_reference(data, packed, compr, cs):
     off_p = off_u = 0
     for z, n in zip(compr.tolist(), cs.tolist()):
@@ -42,7 +50,7 @@ def check_gpu_blocks_with_reference(data, packed, compr, cs):
         off_u += n
 
 
-@pytest.mark.parametrize("kernels", ["v0", "v1", "v2", "v3", "v4", "v5", "v6"])
+@pytest.mark.parametrize("kernels", ["v0", "v1", "v2", "v3", "v4", "v5", "v6", "v7"])
 @pytest.mark.parametrize("chunk", [4096, 65536, 100000, 1 << 20])
 @pytest.mark.parametrize("kind,seed", CORPORA)
 def test_compress_cross_decodes_and_ratio(gpu_ctx, kernels, chunk, kind, seed):
@@ -57,7 +65,7 @@ def test_compress_cross_decodes_and_ratio(gpu_ctx, kernels, chunk, kind, seed):
     assert total <= RATIO_TOLERANCE * int(ref_compr.sum()) + 64, (total, int(ref_compr.sum()))
 
 
-@pytest.mark.parametrize("kernels", ["v0", "v1", "v2", "v3", "v4", "v5", "v6"])
+@pytest.mark.parametrize("kernels", ["v0", "v1", "v2", "v3", "v4", "v5", "v6", "v7"])
 @pytest.mark.parametrize("chunk", [4096, 65536, 100000, 1 << 20])
 @pytest.mark.parametrize("kind,seed", CORPORA)
 def test_decompress_reference_blocks_bit_exact(gpu_ctx, kernels, chunk, kind, seed):
@@ -71,7 +79,7 @@ def test_decompress_reference_blocks_bit_exact(gpu_ctx, kernels, chunk, kind, se
     assert np.array_equal(out, data)
 
 
-@pytest.mark.parametrize("kernels", ["v0", "v1", "v2", "v3", "v4", "v5", "v6"])
+@pytest.mark.parametrize("kernels", ["v0", "v1", "v2", "v3", "v4", "v5", "v6", "v7"])
 def test_small_and_ragged_chunks(gpu_ctx, kernels):
     gpu_ctx.set_option("kernels", kernels)
     rng = np.random.default_rng(5)
@@ -91,7 +99,7 @@ def test_small_and_ragged_chunks(gpu_ctx, kernels):
         assert r == n and np.array_equal(out, data)
 
 
-@pytest.mark.parametrize("kernels", ["v0", "v1", "v2", "v3", "v4", "v5", "v6"])
+@pytest.mark.parametrize("kernels", ["v0", "v1", "v2", "v3", "v4", "v5", "v6", "v7"])
 def test_raw_stored_chunks(gpu_ctx, kernels):
     """compr_sizes[i] == chunk_sizes[i] means raw bytes (_lzbench/lzbench.cpp:311-315)."""
     gpu_ctx.set_option("kernels", kernels)
@@ -107,7 +115,7 @@ def test_raw_stored_chunks(gpu_ctx, kernels):
     assert r == len(data) and np.array_equal(out, data)
 
 
-@pytest.mark.parametrize("kernels", ["v0", "v1", "v2", "v3", "v4", "v5", "v6"])
+@pytest.mark.parametrize("kernels", ["v0", "v1", "v2", "v3", "v4", "v5", "v6", "v7"])
 def test_kat_table_on_gpu(gpu_ctx, kernels):
     gpu_ctx.set_option("kernels", kernels)
     for name, blk, n, expect in O.KATS:
@@ -121,7 +129,7 @@ def test_kat_table_on_gpu(gpu_ctx, kernels):
             assert out.tobytes() == expect, name
 
 
-@pytest.mark.parametrize("kernels", ["v0", "v1", "v2", "v3", "v4", "v5", "v6"])
+@pytest.mark.parametrize("kernels", ["v0", "v1", "v2", "v3", "v4", "v5", "v6", "v7"])
 def test_corrupted_blocks_never_crash_and_match_oracle(gpu_ctx, kernels):
     gpu_ctx.set_option("kernels", kernels)
     rng = np.random.default_rng(13)
@@ -148,7 +156,7 @@ def test_corrupted_blocks_never_crash_and_match_oracle(gpu_ctx, kernels):
             assert np.array_equal(out[i], ref_out), i
 
 
-@pytest.mark.parametrize("kernels", ["v0", "v1", "v2", "v3", "v4", "v5", "v6"])
+@pytest.mark.parametrize("kernels", ["v0", "v1", "v2", "v3", "v4", "v5", "v6", "v7"])
 def test_plugin_signature_wrappers(gpu_ctx, kernels):
     """lzbench_lz4_b200_{init,compress,decompress,deinit}: the unpatched-harness path, one chunk per call."""
     wm = L.lib.lzbench_lz4_b200_init(65536, 0, 0)
@@ -182,7 +190,7 @@ def test_output_capacity_rule(gpu_ctx):
     assert total == 0
 
 
-@pytest.mark.parametrize("kernels", ["v0", "v1", "v2", "v3", "v4", "v5", "v6"])
+@pytest.mark.parametrize("kernels", ["v0", "v1", "v2", "v3", "v4", "v5", "v6", "v7"])
 def test_device_resident_roundtrip_256m(gpu_ctx, kernels):
     """Full-size property test: encode -> decode on the device, compare CRC of the whole image."""
     import torch
@@ -331,3 +339,76 @@ def test_segment_boundary_chunk_sizes(gpu_ctx):
         check_gpu_blocks_with_reference(data, packed[:total], compr, cs)
         out, r = gpu_ctx.decompress_batch(packed[:total], compr, cs)
         assert r == n and np.array_equal(out, data)
+
+
+def _dependency_stress(n, seed):
+    """Data that exercises what the lane-per-sequence decoder (v7) does inside a group of 32 sequences: records that
+    copy from the previous record (chains for source forwarding), short periodic runs (overlapping matches executed by
+    one lane), matches that straddle literal/match boundaries, literal runs and matches around the 64-byte lane limit."""
+    rng = np.random.default_rng(seed)
+    out = np.empty(n, dtype=np.uint8)
+    pos = 0
+    words = [rng.integers(97, 123, int(rng.integers(2, 12))).astype(np.uint8) for _ in range(300)]
+    while pos < n:
+        kind = int(rng.integers(0, 7))
+        if kind == 0:                                    # records: counter + constant + noise, 8..40 bytes each
+            rl = int(rng.integers(8, 41)); cnt = int(rng.integers(4, 200))
+            rec = rng.integers(0, 256, rl).astype(np.uint8)
+            buf = np.tile(rec, cnt).reshape(cnt, rl)
+            buf[:, 0] = np.arange(cnt) & 255
+            if rl > 12: buf[:, rl // 2] = rng.integers(0, 256, cnt)
+            b = buf.reshape(-1)
+        elif kind == 1:                                  # short periodic runs: period 1..7, length 5..80
+            parts = []
+            for _ in range(int(rng.integers(4, 60))):
+                per = int(rng.integers(1, 8)); ln = int(rng.integers(5, 81))
+                parts.append(np.resize(rng.integers(0, 256, per).astype(np.uint8), ln))
+                parts.append(rng.integers(0, 256, int(rng.integers(0, 6))).astype(np.uint8))
+            b = np.concatenate(parts)
+        elif kind == 2:                                  # text from a small vocabulary
+            b = np.concatenate([np.append(words[int(i)], 32) for i in rng.zipf(1.3, int(rng.integers(20, 400))) % len(words)]).astype(np.uint8)
+        elif kind == 3:                                  # literal runs around the lane limit
+            b = rng.integers(0, 256, int(rng.integers(56, 75))).astype(np.uint8)
+        elif kind == 4 and pos > 200:                    # a copy of earlier output, 56..74 bytes or long, near or far
+            ln = int(rng.integers(56, 75)) if rng.integers(0, 2) else int(rng.integers(100, 3000))
+            back = int(rng.integers(ln, min(pos, 65000) + 1)) if pos > ln else pos
+            b = out[pos - back:pos - back + ln].copy()
+        elif kind == 5:                                  # long runs
+            b = np.full(int(rng.integers(64, 5000)), int(rng.integers(0, 256)), dtype=np.uint8)
+        else:
+            b = rng.integers(0, 256, int(rng.integers(1, 600))).astype(np.uint8)
+        b = b[:n - pos]
+        out[pos:pos + len(b)] = b
+        pos += len(b)
+    return out
+
+
+@pytest.mark.parametrize("kernels", ["v5", "v7"])
+@pytest.mark.parametrize("seed", [21, 22, 23])
+def test_dependency_stress_blocks(gpu_ctx, kernels, seed):
+    gpu_ctx.set_option("kernels", kernels)
+    n = 6 * (1 << 20) + 4321
+    data = _dependency_stress(n, seed)
+    for chunk in (65536, 16384, 3000):
+        cs = L.chunk_list(n, chunk)
+        packed, compr = O.oracle_chunked_compress(data, cs)
+        out, r = gpu_ctx.decompress_batch(packed, compr, cs)
+        assert r == n
+        bad = np.flatnonzero(out != data)
+        assert bad.size == 0, (chunk, int(bad[0]), int(bad[0]) // chunk, int(bad[0]) % chunk)
+        packed, compr, total = gpu_ctx.compress_batch(data, cs)
+        out, r = gpu_ctx.decompress_batch(packed[:total], compr, cs)
+        assert r == n and np.array_equal(out, data)
+
+
+def test_v7_unaligned_output_and_input(gpu_ctx):
+    """The lane-per-sequence decoder flushes its window with 16-byte stores relative to the chunk start rounded down to
+    16 bytes: every misalignment of the output and of the compressed stream."""
+    data = L.corpus("mixed", 400000, seed=12)
+    for lead in range(0, 17):
+        sizes = [lead + 1] + [20000 + 3 * lead, 65536, 31, 65535, 50000]
+        cs = np.asarray(sizes, dtype=np.uint64)
+        n = int(cs.sum())
+        packed, compr = O.oracle_chunked_compress(data[:n], cs)
+        out, r = gpu_ctx.decompress_batch(packed, compr, cs)
+        assert r == n and np.array_equal(out, data[:n]), lead
