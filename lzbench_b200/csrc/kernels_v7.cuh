@@ -4,10 +4,11 @@
 // v5 spends 155 warp instructions per iteration on 4 sequences of ~16 bytes and is issue-bound (profiles/r01_*).
 // The chain itself is cheap -- token -> literal length -> next token -- it is the copies that need the lanes.  So:
 //
-//  1. parse_v7_kernel: one lane per CHUNK walks the chain, validates every rule the reference decoder enforces
-//     (the same checks, in the same order, as the general path of v5) and writes one 8-byte entry per sequence:
-//     output position, position of the literals in the stream, offset, literal count.  32 chunks per warp
-//     instruction; the kernel is latency-bound (a few warps per SM) and leaves the machine to its neighbour.
+//  1. parse_v7_kernel: one lane per CHUNK walks the chain, checks every rule of the reference decoder that concerns
+//     lengths and positions (lz4/lz4.c:1797-2151; the same checks as the general path of v5) and writes one 8-byte
+//     entry per sequence: output position, literal count, position of the literals in the stream, match length.
+//     32 chunks per warp instruction; the kernel is latency-bound (a few warps per SM).  The offsets are not on the
+//     chain: they are read and checked in pass 2, one lane per sequence.
 //  2. decompress_v7_kernel: one warp per chunk, 32 consecutive sequences per step, one lane each.  All literal
 //     runs of a group are independent; matches depend only on earlier output.  Output goes to a per-warp linear
 //     window in shared memory (the group's span plus ~1 KiB of history) and is flushed to global memory in
@@ -39,7 +40,8 @@ constexpr u32 V7_ROUTE_NONE = 0, V7_ROUTE_SEQ = 1, V7_ROUTE_TEAM = 2;
 // entries of the table a chunk may need: sequences (>= 4 output bytes each but the last), literal pieces, terminator
 __host__ __device__ inline u64 v7_entries_for(u64 out_bytes, u64 chunks)
 {
-    return out_bytes / 4 + out_bytes / V7_LPIECE + 3 * chunks;
+    // per chunk of n bytes: <= n/4 sequences with a match, the last one, <= n/8191 literal pieces, the terminator
+    return out_bytes / 4 + out_bytes / 4096 + 4 * chunks;
 }
 
 struct V7Params {
@@ -52,86 +54,178 @@ struct V7Params {
     u32* team_list; u32* team_count;       // chunks left to the team decoder
 };
 
-// entry: bits 0-16 output position of the sequence, 17-33 stream position of its literals, 34-49 offset (0: no match),
-//        50-62 literal count
-__device__ __forceinline__ u64 v7_pack(u32 op, u32 lsrc, u32 off, u32 L)
+// entry, low word: bits 0-16 output position of the sequence, 17-29 literal count; high word: bits 0-15 stream position
+// of its literals (chunks whose stream is 64 KiB or longer go to the team decoder), 16-31 match length (0: no match; the
+// two offset bytes follow the literals)
+__device__ __forceinline__ u64 v7_pack(u32 op, u32 lsrc, u32 M, u32 L)
 {
-    return (u64)op | ((u64)lsrc << 17) | ((u64)off << 34) | ((u64)L << 50);
+    return (u64)(op | (L << 17)) | ((u64)(lsrc | (M << 16)) << 32);
 }
 
 // ---- pass 1: the token chain, one lane per chunk ---------------------------------------------------------------
+// A warp step waits for its slowest lane, so nothing in the loop may be slow for ANY lane:
+//  * 32 independent streams miss L1 somewhere in almost every step (first build: 2300 cycles per step,
+//    profiles/r02_parse_*): every lane reads its stream through its own ring in shared memory, filled by cp.async
+//    16 bytes at a time ahead of the read position (LDGSTS, as v5 does per team);
+//  * nothing waits for memory: a lane whose bytes have not landed sits the step out, and a literal run that leaves
+//    the ring restarts the ring behind it and waits for it the same way (V7M_WAITQ);
+//  * the common sequence (length nibbles complete or one extension byte below 255, not near the end of the block,
+//    every length rule satisfied) is decoded without a branch: token -> literal count -> match length byte -> next
+//    token; everything else goes through the general code, which repeats the checks of the reference decoder in
+//    its order and names the violated rule.
+constexpr u32 V7_RING = 512;               // bytes of stream per lane in shared memory (+ 16: the first block again, so that short reads never wrap)
+constexpr u32 V7_LOOK = 352;               // blocks are requested up to this far ahead of the read position
+constexpr u32 V7_G = 4;                    // steps between a request and the first read that may rely on it
+enum : u32 { V7M_TOKEN = 0, V7M_WAITQ = 1, V7M_IDLE = 2 };
+
+__device__ __forceinline__ void v7_cp16(u8* smem_dst, const u8* gsrc)
+{
+    const u32 d = (u32)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(d), "l"(gsrc) : "memory");
+}
+
 __global__ void __launch_bounds__(32)
 parse_v7_kernel(const __grid_constant__ V7Params P)
 {
-    const u32 c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= P.n_chunks) return;
-    const u8* __restrict__ src = P.in + P.in_off[c];
-    const u64 clen64 = P.csz[c], n64 = P.usz[c];
-    const u64 rel = P.out_off[c] - P.out_off[0];
-    const u64 base = v7_entries_for(rel, c);
-    u32 err = ST_OK, route = V7_ROUTE_SEQ, k = 0;
-    if (clen64 == n64) {
-        route = n64 >= 4096 ? V7_ROUTE_TEAM : V7_ROUTE_SEQ;            // raw chunk (_lzbench/lzbench.cpp:311-315): a plain copy
-    } else if (n64 > V7_MAX_CHUNK || clen64 > 0x1FFFFu || base + v7_entries_for(n64, 1) > P.table_cap) {
-        route = V7_ROUTE_TEAM;
-    } else {
-        const u32 clen = (u32)clen64, n = (u32)n64;
-        const u32 capv = P.cap_all > n ? P.cap_all : n;
-        u64* __restrict__ tab = P.table + base;
-        u32 ip = 0, op = 0;
-        if (n == 0 || clen == 0) {                                       // lz4/lz4.c:1776-1782
-            err = (n == 0 && clen == 1 && src[0] == 0) ? ST_OK : ST_EMPTY;
-            route = V7_ROUTE_NONE;
-        } else for (;;) {
-            if (ip >= clen) { err = ST_TOKEN_OOB; break; }
-            const u32 token = src[ip++];
-            u32 len = token >> 4;
-            if (len == RUN_MASK) {                                       // lz4/lz4.c:1707-1729 read_variable_length
-                if (ip + RUN_MASK >= clen) { err = ST_LITLEN_OOB; break; }
-                u32 s;
-                do {
-                    s = src[ip++]; len += s;
-                    if (s == 255 && ip + RUN_MASK >= clen) { err = ST_LITLEN_OOB; break; }
-                } while (s == 255);
-                if (err) break;
+    __shared__ __align__(16) u8 ring_all[32][V7_RING + 16];
+    const u32 c = blockIdx.x * 32 + threadIdx.x;
+    const bool have = c < P.n_chunks;
+    u32 err = ST_OK, route = V7_ROUTE_NONE, k = 0;
+    u32 mode = V7M_IDLE;
+    const u8* srcA = nullptr;              // the stream, from its start rounded down to 16 bytes: positions below count from here
+    u64* tab = nullptr;
+    u32 clen = 0, n = 0, capv = 0, mis = 0, ip = 0, op = 0;
+    if (have) {
+        const u8* src = P.in + P.in_off[c];
+        const u64 clen64 = P.csz[c], n64 = P.usz[c];
+        const u64 base = v7_entries_for(P.out_off[c] - P.out_off[0], c);
+        if (clen64 == n64) {
+            route = n64 >= 4096 ? V7_ROUTE_TEAM : V7_ROUTE_SEQ;        // raw chunk (_lzbench/lzbench.cpp:311-315): a plain copy
+        } else if (n64 > V7_MAX_CHUNK || clen64 > 0xFFFFu || base + v7_entries_for(n64, 1) > P.table_cap) {
+            route = V7_ROUTE_TEAM;
+        } else if (n64 == 0 || clen64 == 0) {                            // lz4/lz4.c:1776-1782
+            err = (n64 == 0 && clen64 == 1 && src[0] == 0) ? ST_OK : ST_EMPTY;
+        } else {
+            mis = (u32)(reinterpret_cast<uintptr_t>(src) & 15u);
+            srcA = src - mis; clen = (u32)clen64 + mis; n = (u32)n64; ip = mis;
+            capv = P.cap_all > n ? P.cap_all : n;
+            tab = P.table + base;
+            route = V7_ROUTE_SEQ; mode = V7M_TOKEN;
+        }
+    }
+    u8* const ring = ring_all[threadIdx.x];
+    u32 req = 0;                           // blocks below this position have been requested (multiple of 16)
+    u32 landed = 0, pend = 0;              // positions below `landed` have arrived
+    u32 rlo = 0;                           // ... and are in the ring if not below its last restart (and not yet overwritten: see V7_RD)
+    u32 wtok = 0, wL = 0, wlsrc = 0;       // V7M_WAITQ: token, literal count and literal position of the sequence that waits for what follows its literals
+#define V7_RING_AT(POS) ring[(POS) & (V7_RING - 1)]
+#define V7_RD(POS) ((POS) < landed && (POS) >= rlo && (POS) + V7_RING >= req ? (u32)V7_RING_AT(POS) : (u32)__ldg(srcA + (POS)))
+#define V7_REQUEST() do { v7_cp16(&V7_RING_AT(req), srcA + req); if ((req & (V7_RING - 1)) == 0) v7_cp16(ring + V7_RING, srcA + req); req += 16; } while (0)
+    if (mode == V7M_TOKEN) {
+        while (req < V7_RING && req < clen) V7_REQUEST();
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    landed = pend = req;
+    for (u32 it = 1; __any_sync(FULL, mode != V7M_IDLE); it++) {
+        // ---- ring upkeep: at most two blocks per step (a step consumes ~10 bytes), readable V7_G .. 2 V7_G steps later ----
+        {
+            const u32 cons = mode == V7M_WAITQ ? wlsrc + wL : ip;
+            if (mode != V7M_IDLE && req < clen && req < cons + V7_LOOK) {
+                if (cons >= req + 16) {                                   // the chain jumped past everything requested: restart there,
+                    if (landed == req) req = rlo = cons & ~15u;           // once nothing is in flight (a slot must not have two copies pending)
+                } else {                                                  // (req + 16 <= (cons & ~15) + V7_RING follows from req < cons + V7_LOOK)
+                    V7_REQUEST();
+                    if (req < clen && req < cons + 96) V7_REQUEST();      // behind after a restart: two per step
+                }
             }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            asm volatile("cp.async.wait_group %0;" :: "n"(V7_G) : "memory");
+            if (it % V7_G == 0) { landed = pend; pend = req; }
+        }
+        // ---- common case, no branch ----
+        const u8* ra = ring + (ip & (V7_RING - 1));
+        const u32 token = ra[0], e1 = ra[1];                             // (whatever is there if it has not landed: checked below)
+        const bool lx = (token >> 4) == RUN_MASK;
+        const u32 Lf = lx ? RUN_MASK + e1 : token >> 4;
+        const u32 lsrc_f = ip + (lx ? 2u : 1u);
+        const u32 q = lsrc_f + Lf;                                        // position of the offset
+        const u32 m1 = V7_RING_AT(q + 2);
+        const bool mx = (token & ML_MASK) == ML_MASK;
+        const u32 ml_f = (mx ? ML_MASK + m1 : token & ML_MASK) + MINMATCH;
+        const u32 cpy_f = op + Lf, nop_f = cpy_f + ml_f;
+        const bool fast = mode == V7M_TOKEN && q + 3 <= landed && q + (2 + 1 + LASTLITERALS) <= clen && !(lx && e1 == 255) &&
+                          !(mx && m1 == 255) && cpy_f + MFLIMIT <= capv && nop_f + LASTLITERALS <= capv && nop_f <= n;
+        if (fast) {
+            tab[k++] = v7_pack(op, lsrc_f - mis, ml_f, Lf);
+            op = nop_f;
+            ip = q + (mx ? 3u : 2u);
+        }
+        // ---- everything else: one sequence through the general code, when its bytes are there (else the lane sits this step out) ----
+        // TOKEN: 32 bytes from the token on must have landed (token, length bytes; longer runs of length bytes read global memory)
+        // unless the stream ends first.  What follows a long literal run is asked for through WAITQ.
+        const bool go = !fast && ((mode == V7M_TOKEN && (ip + 32 <= landed || (ip + 32 > clen && landed >= clen))) ||
+                                  (mode == V7M_WAITQ && (wlsrc + wL + 32 <= landed || landed >= clen)));
+        if (go) do {
+            u32 tk, len, lsrc;
+            if (mode == V7M_TOKEN) {
+                if (ip >= clen) { err = ST_TOKEN_OOB; mode = V7M_IDLE; break; }
+                tk = V7_RD(ip); ip++;
+                len = tk >> 4;
+                if (len == RUN_MASK) {                                   // lz4/lz4.c:1707-1729 read_variable_length
+                    if (ip + RUN_MASK >= clen) { err = ST_LITLEN_OOB; mode = V7M_IDLE; break; }
+                    u32 s;
+                    do {
+                        s = V7_RD(ip); ip++; len += s;
+                        if (s == 255 && ip + RUN_MASK >= clen) { err = ST_LITLEN_OOB; break; }
+                    } while (s == 255);
+                    if (err) { mode = V7M_IDLE; break; }
+                }
+                lsrc = ip;
+                const u32 qq = ip + len;
+                if (qq + 32 > landed && landed < clen && qq + (2 + 1 + LASTLITERALS) <= clen && op + len + MFLIMIT <= capv) {
+                    wtok = tk; wL = len; wlsrc = lsrc; mode = V7M_WAITQ;  // what follows the literals is not there yet: ask for it, come back
+                    break;
+                }
+            } else { tk = wtok; len = wL; lsrc = wlsrc; ip = lsrc; }
+            mode = V7M_IDLE;                                              // set back when the sequence is complete and not the last
             const u32 cpy = op + len;                                    // len < 255 * clen: no wrap
             const bool last = cpy + MFLIMIT > capv || ip + len + (2 + 1 + LASTLITERALS) > clen;
             if (last && (ip + len != clen || cpy > n)) { err = ST_LAST_LITERALS; break; }
             if (cpy > n) { err = ST_MATCH_END; break; }                  // (frame capacity > n) rejected below anyway; keeps the entry count bounded by n
-            u32 lsrc = ip, L = len, lop = op;
-            while (L > V7_LPIECE) {                                      // literal-only pieces
-                tab[k++] = v7_pack(lop, lsrc, 0, V7_LPIECE);
-                lop += V7_LPIECE; lsrc += V7_LPIECE; L -= V7_LPIECE;
+            u32 ls = lsrc - mis, Lr = len, lop = op;
+            while (Lr > V7_LPIECE) {                                     // literal-only pieces
+                tab[k++] = v7_pack(lop, ls, 0, V7_LPIECE);
+                lop += V7_LPIECE; ls += V7_LPIECE; Lr -= V7_LPIECE;
             }
             if (last) {
-                tab[k++] = v7_pack(lop, lsrc, 0, L);
+                tab[k++] = v7_pack(lop, ls, 0, Lr);
                 op = cpy;
                 if (op != n) err = ST_SIZE;
                 break;
             }
-            const u32 off = (u32)src[ip + len] | ((u32)src[ip + len + 1] << 8);
-            ip += len + 2; op = cpy;
-            u32 ml = token & ML_MASK;
-            if (ml == ML_MASK) {
+            ip += len + 2; op = cpy;                                     // the offset itself is read and checked in pass 2
+            u32 m = tk & ML_MASK;
+            if (m == ML_MASK) {
                 u32 s;
                 do {
-                    s = src[ip++]; ml += s;
+                    s = V7_RD(ip); ip++; m += s;
                     if (ip + LASTLITERALS - 1 >= clen) { err = ST_MATCHLEN_OOB; break; }
                 } while (s == 255);
                 if (err) break;
             }
-            ml += MINMATCH;
-            if (off == 0 || off > op) { err = ST_OFFSET; break; }
-            if (op + ml + LASTLITERALS > capv || op + ml > n) { err = ST_MATCH_END; break; }
-            tab[k++] = v7_pack(lop, lsrc, off, L);
-            op += ml;
-        }
-        if (!err && route == V7_ROUTE_SEQ) {
-            tab[k] = v7_pack(n, 0, 0, 0);                                // terminator: carries the end position
-            if ((u64)k * 256 < n) route = V7_ROUTE_TEAM;                 // mostly long copies: the team decoder's case
-        }
+            m += MINMATCH;
+            if (op + m + LASTLITERALS > capv || op + m > n) { err = ST_MATCH_END; break; }
+            tab[k++] = v7_pack(lop, ls, m, Lr);
+            op += m;
+            mode = V7M_TOKEN;
+        } while (0);
     }
+#undef V7_RD
+#undef V7_RING_AT
+#undef V7_REQUEST
+    if (!have) return;
+    if (!err && route == V7_ROUTE_SEQ && (u64)k * 256 < n) route = V7_ROUTE_TEAM;     // mostly long copies: the team decoder's case
     if (err) route = V7_ROUTE_NONE;
     P.status[c] = err;
     P.nseq[c] = k;
@@ -201,21 +295,31 @@ decompress_v7_kernel(const __grid_constant__ V7Params P)
         u32 win_base = 0;                  // position of win[0]; multiple of 16
         u32 flushed = A;                   // positions below are in global memory
         u32 cur = 0;
+        bool bad = false;                  // an offset of this chunk points before its start (or is 0)
+        u64 e_next = lane < ns ? tab[lane] : 0ull;
 
         while (cur < ns) {
-            const u32 idx = cur + lane;
-            const bool valid = idx < ns;
-            const u64 e0 = valid ? tab[idx] : 0ull, e1 = valid ? tab[idx + 1] : 0ull;
-            const u32 op = ((u32)e0 & 0x1FFFFu) + A;
-            const u32 lsrc = (u32)(e0 >> 17) & 0x1FFFFu;
-            const u32 off = (u32)(e0 >> 34) & 0xFFFFu;
-            const u32 L = (u32)(e0 >> 50) & 0x1FFFu;
-            const u32 opn = ((u32)e1 & 0x1FFFFu) + A;
-            const u32 M = valid ? opn - op - L : 0u;
+            const bool valid = cur + lane < ns;
+            const u64 e = e_next;
+            const u32 op = ((u32)e & 0x1FFFFu) + A;
+            const u32 L = (u32)e >> 17;
+            const u32 lsrc = (u32)(e >> 32) & 0xFFFFu;
+            const u32 M = (u32)(e >> 48);
+            const u32 opn = op + L + M;
+            u32 off = 0;
+            if (valid && M) off = (u32)__ldg(src + lsrc + L) | ((u32)__ldg(src + lsrc + L + 1) << 8);
             const u32 op0 = __shfl_sync(FULL, op, 0);
             const bool lng = valid && (L > V7_CAP || M > V7_CAP);
             const unsigned stop = __ballot_sync(FULL, !valid || lng || opn - op0 > V7_SPAN);
             const u32 k = stop ? (u32)__ffs(stop) - 1u : 32u;          // lanes [0, k) form the group
+            const bool lng_k = k < 32 && __shfl_sync(FULL, (u32)lng, k & 31);       // ... and a long sequence follows it
+            {   // the next group's entries: on their way while this one is executed
+                const u32 nx = cur + k + (lng_k ? 1u : 0u) + lane;
+                e_next = nx < ns ? tab[nx] : 0ull;
+            }
+            // the offset rule (lz4/lz4.c:1764 checkOffset; offset 0 rejected as in the oracle): a bad one makes the chunk bad
+            const bool off_bad = valid && M && (off == 0 || off > op - A + L);
+            if (__any_sync(FULL, off_bad && lane <= k)) bad = true;
             if (k) {
                 const bool act = lane < k;
                 const u32 opend = __shfl_sync(FULL, opn, k - 1);
@@ -250,7 +354,7 @@ decompress_v7_kernel(const __grid_constant__ V7Params P)
                     }
                 }
                 // ---- matches ----
-                const bool hasm = act && M != 0;
+                const bool hasm = act && M != 0 && !off_bad;
                 const bool ovl = off < M;                               // overlapping: periodic extension, copied serially by its lane
                 const u32 dstm = op + L;
                 const u32 key = act ? op : 0xFFFFFFFFu;                 // sorted over the lanes of the group
@@ -278,22 +382,21 @@ decompress_v7_kernel(const __grid_constant__ V7Params P)
                         if (can) shift += sj;
                     }
                     // dependencies: earlier matches of the group whose output intersects [s, e)
-                    const u32 s = dstm - shift, e = s + (ovl ? off : M);
+                    const u32 s = dstm - shift, e2 = s + (ovl ? off : M);
                     ja = 0; u32 jb = 0;
                     #pragma unroll
                     for (u32 st = 16; st; st >>= 1) {
                         const u32 ta = __shfl_sync(FULL, key, ja | st);
                         const u32 tb = __shfl_sync(FULL, key, jb | st);
                         if (ta <= s) ja |= st;
-                        if (tb <= e - 1) jb |= st;
+                        if (tb <= e2 - 1) jb |= st;
                     }
                     const unsigned mb = __ballot_sync(FULL, hasm);
                     const u32 da = __shfl_sync(FULL, dstm, ja), db = __shfl_sync(FULL, dstm, jb);
-                    if (hasm && e > op0) {
-                        const u32 lo = s >= op0 ? ja : 0u;
-                        unsigned range = (jb >= 31 ? FULL : ((2u << jb) - 1u)) & ~((1u << lo) - 1u);
-                        if (da >= e) range &= ~(1u << lo);
-                        if (db >= e) range &= ~(1u << jb);
+                    if (hasm && e2 > op0) {
+                        unsigned range = (jb >= 31 ? FULL : ((2u << jb) - 1u)) & ~((1u << ja) - 1u);
+                        if (da >= e2) range &= ~(1u << ja);
+                        if (db >= e2) range &= ~(1u << jb);
                         depmask = range & mb & lt_mask;
                     }
                 }
@@ -346,9 +449,10 @@ decompress_v7_kernel(const __grid_constant__ V7Params P)
                 cur += k;
             }
             // ---- a long sequence: whole warp, through global memory ----
-            if (k < 32 && (stop >> k & 1u) && __shfl_sync(FULL, (u32)lng, k)) {
+            if (lng_k) {
                 const u32 l_op = __shfl_sync(FULL, op, k), l_src = __shfl_sync(FULL, lsrc, k), l_L = __shfl_sync(FULL, L, k);
-                const u32 l_M = __shfl_sync(FULL, M, k), l_off = __shfl_sync(FULL, off, k), l_end = __shfl_sync(FULL, opn, k);
+                const u32 l_off = __shfl_sync(FULL, off, k), l_end = __shfl_sync(FULL, opn, k);
+                const u32 l_M = __shfl_sync(FULL, off_bad ? 0u : M, k);
                 v7_flush(dstv, win, win_base, flushed, l_op, true, lane);
                 __syncwarp();
                 if (l_L) { coop_copy(dstv + l_op, src + l_src, l_L, lane, 32); __syncwarp(); }
@@ -367,6 +471,10 @@ decompress_v7_kernel(const __grid_constant__ V7Params P)
         }
         v7_flush(dstv, win, win_base, flushed, n + A, true, lane);
         __syncwarp();
+        if (bad && lane == 0) {
+            P.status[c] = ST_OFFSET;
+            if (P.bad_chunks) atomicAdd(P.bad_chunks, 1u);
+        }
     }
 }
 

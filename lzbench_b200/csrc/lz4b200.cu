@@ -207,7 +207,7 @@ void ensure_v7(lz4b200_ctx* c, size_t n, size_t table_chunks, size_t max_chunk)
 {
     c->v7_chunks = c->v7_table_chunks = 0;
     if (c->kernel_gen != 7 || max_chunk > V7_MAX_CHUNK || n == 0) return;
-    c->v7_per_chunk = (size_t)v7_entries_for(max_chunk, 1);
+    c->v7_per_chunk = (size_t)v7_entries_for(max_chunk, 1) + 2;      // + 2: the floors of a ragged prefix sum
     if (c->v7_u32.ensure(3 * n * sizeof(u32)) != cudaSuccess ||
         c->v7_table.ensure(table_chunks * c->v7_per_chunk * sizeof(u64)) != cudaSuccess) { cudaGetLastError(); return; }
     c->v7_chunks = n; c->v7_table_chunks = table_chunks;
