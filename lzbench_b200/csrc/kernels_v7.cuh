@@ -74,7 +74,7 @@ __device__ __forceinline__ u64 v7_pack(u32 op, u32 lsrc, u32 M, u32 L)
 //    token; everything else goes through the general code, which repeats the checks of the reference decoder in
 //    its order and names the violated rule.
 constexpr u32 V7_RING = 512;               // bytes of stream per lane in shared memory (+ 16: the first block again, so that short reads never wrap)
-constexpr u32 V7_LOOK = 352;               // blocks are requested up to this far ahead of the read position
+constexpr u32 V7_LOOK = 384;               // blocks are requested up to this far ahead of the read position
 constexpr u32 V7_G = 4;                    // steps between a request and the first read that may rely on it
 enum : u32 { V7M_TOKEN = 0, V7M_WAITQ = 1, V7M_IDLE = 2 };
 
@@ -127,45 +127,56 @@ parse_v7_kernel(const __grid_constant__ V7Params P)
     asm volatile("cp.async.commit_group;" ::: "memory");
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     landed = pend = req;
+    u32 tok = V7_RING_AT(ip), te1 = V7_RING_AT(ip + 1);                  // token at ip and the byte behind it
+    bool tv = mode == V7M_TOKEN && ip + 2 <= landed;                    // ... if they had landed when they were read
+    // limits of the common case: the offset position q must satisfy q + 3 <= landed and q + 8 <= clen (not the last sequence,
+    // lz4/lz4.c:1990), the literal end cpy + MFLIMIT <= capv, the match end <= n and + LASTLITERALS <= capv
+    const bool tiny = capv < 32 || clen < 32;                             // everything through the general code
+    const u32 lim_cpy = tiny ? 0u : capv - MFLIMIT;
+    const u32 lim_nop = tiny ? 0u : (n < capv - LASTLITERALS ? n : capv - LASTLITERALS);
+    u32 qlim = tiny ? 0u : (clen < landed + 5 ? clen : landed + 5) - 8;
     for (u32 it = 1; __any_sync(FULL, mode != V7M_IDLE); it++) {
-        // ---- ring upkeep: at most two blocks per step (a step consumes ~10 bytes), readable V7_G .. 2 V7_G steps later ----
-        {
+        // ---- ring upkeep every V7_G steps: up to six blocks (a step consumes ~10 bytes), readable V7_G .. 2 V7_G steps later ----
+        if (it % V7_G == 0) {
             const u32 cons = mode == V7M_WAITQ ? wlsrc + wL : ip;
             if (mode != V7M_IDLE && req < clen && req < cons + V7_LOOK) {
                 if (cons >= req + 16) {                                   // the chain jumped past everything requested: restart there,
                     if (landed == req) req = rlo = cons & ~15u;           // once nothing is in flight (a slot must not have two copies pending)
                 } else {                                                  // (req + 16 <= (cons & ~15) + V7_RING follows from req < cons + V7_LOOK)
-                    V7_REQUEST();
-                    if (req < clen && req < cons + 96) V7_REQUEST();      // behind after a restart: two per step
+                    for (u32 j = 0; j < 6 && req < clen && req < cons + V7_LOOK; j++) V7_REQUEST();
                 }
             }
             asm volatile("cp.async.commit_group;" ::: "memory");
-            asm volatile("cp.async.wait_group %0;" :: "n"(V7_G) : "memory");
-            if (it % V7_G == 0) { landed = pend; pend = req; }
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+            landed = pend; pend = req;
+            qlim = tiny ? 0u : (clen < landed + 5 ? clen : landed + 5) - 8;
         }
-        // ---- common case, no branch ----
-        const u8* ra = ring + (ip & (V7_RING - 1));
-        const u32 token = ra[0], e1 = ra[1];                             // (whatever is there if it has not landed: checked below)
-        const bool lx = (token >> 4) == RUN_MASK;
-        const u32 Lf = lx ? RUN_MASK + e1 : token >> 4;
+        // ---- common case, no branch.  The token (and the byte behind it) of the CURRENT position were read one step ago
+        //      (tok, te1, valid iff tv): this step reads the match length byte and, at the position the chain moves to if the
+        //      sequence is a common one, the next token. ----
+        const bool lx = (tok >> 4) == RUN_MASK;
+        const u32 Lf = lx ? RUN_MASK + te1 : tok >> 4;
         const u32 lsrc_f = ip + (lx ? 2u : 1u);
         const u32 q = lsrc_f + Lf;                                        // position of the offset
+        const bool mx = (tok & ML_MASK) == ML_MASK;
+        const u32 ipn = q + (mx ? 3u : 2u);
         const u32 m1 = V7_RING_AT(q + 2);
-        const bool mx = (token & ML_MASK) == ML_MASK;
-        const u32 ml_f = (mx ? ML_MASK + m1 : token & ML_MASK) + MINMATCH;
+        const u8* rn = ring + (ipn & (V7_RING - 1));
+        const u32 tokn = rn[0], e1n = rn[1];                              // (whatever is there if it has not landed: tv says)
+        const u32 ml_f = (mx ? ML_MASK + m1 : tok & ML_MASK) + MINMATCH;
         const u32 cpy_f = op + Lf, nop_f = cpy_f + ml_f;
-        const bool fast = mode == V7M_TOKEN && q + 3 <= landed && q + (2 + 1 + LASTLITERALS) <= clen && !(lx && e1 == 255) &&
-                          !(mx && m1 == 255) && cpy_f + MFLIMIT <= capv && nop_f + LASTLITERALS <= capv && nop_f <= n;
-        if (fast) {
+        const bool fast = tv && q <= qlim && cpy_f <= lim_cpy && nop_f <= lim_nop && !(lx && te1 == 255) && !(mx && m1 == 255);
+        if (fast) {                                                       // (tv is only ever set in V7M_TOKEN)
             tab[k++] = v7_pack(op, lsrc_f - mis, ml_f, Lf);
             op = nop_f;
-            ip = q + (mx ? 3u : 2u);
+            ip = ipn; tok = tokn; te1 = e1n; tv = ipn + 2 <= landed;
         }
         // ---- everything else: one sequence through the general code, when its bytes are there (else the lane sits this step out) ----
         // TOKEN: 32 bytes from the token on must have landed (token, length bytes; longer runs of length bytes read global memory)
         // unless the stream ends first.  What follows a long literal run is asked for through WAITQ.
-        const bool go = !fast && ((mode == V7M_TOKEN && (ip + 32 <= landed || (ip + 32 > clen && landed >= clen))) ||
-                                  (mode == V7M_WAITQ && (wlsrc + wL + 32 <= landed || landed >= clen)));
+        if (!fast && mode != V7M_IDLE) {
+        const bool go = (mode == V7M_TOKEN && (ip + 32 <= landed || (ip + 32 > clen && landed >= clen))) ||
+                        (mode == V7M_WAITQ && (wlsrc + wL + 32 <= landed || landed >= clen));
         if (go) do {
             u32 tk, len, lsrc;
             if (mode == V7M_TOKEN) {
@@ -220,6 +231,11 @@ parse_v7_kernel(const __grid_constant__ V7Params P)
             op += m;
             mode = V7M_TOKEN;
         } while (0);
+        {                                                                 // the general code moved ip, or the token had not landed: read it (again)
+            const u8* ra = ring + (ip & (V7_RING - 1));
+            tok = ra[0]; te1 = ra[1]; tv = mode == V7M_TOKEN && ip + 2 <= landed && ip >= rlo;
+        }
+        }
     }
 #undef V7_RD
 #undef V7_RING_AT
