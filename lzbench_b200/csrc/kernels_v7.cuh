@@ -35,6 +35,8 @@ constexpr u32 V7_KEEP = 1008;              // history kept below a group when th
 constexpr u32 V7_LPIECE = 8191;            // literal runs are cut into entries of at most this many bytes (13-bit field)
 constexpr u32 V7_MAX_CHUNK = 65536;
 constexpr int V7_WARPS = 8;                // warps per CTA of the lane-per-sequence kernel
+constexpr u32 V7_STAGE = 1024;             // stream bytes staged per group (two 16-byte blocks per lane)
+constexpr u32 V7_WARP_SMEM = 4096 + 32 + 2 * 1024;   // V7_WIN + 32 + 2 * V7_STAGE
 constexpr u32 V7_ROUTE_NONE = 0, V7_ROUTE_SEQ = 1, V7_ROUTE_TEAM = 2;
 
 // entries of the table a chunk may need: sequences (>= 4 output bytes each but the last), literal pieces, terminator
@@ -288,9 +290,11 @@ __device__ __forceinline__ void v7_flush(u8* dstv, const u8* win, u32 win_base, 
 __global__ void __launch_bounds__(V7_WARPS * 32, 3)
 decompress_v7_kernel(const __grid_constant__ V7Params P)
 {
-    __shared__ __align__(16) u8 win_all[V7_WARPS][V7_WIN + 32];
+    // per warp: the output window, then two buffers for the stream bytes of the next group (on their way while this one runs)
+    extern __shared__ __align__(16) u8 v7_smem[];
     const u32 lane = lane_id();
-    u8* const win = win_all[threadIdx.x >> 5];
+    u8* const win = v7_smem + (threadIdx.x >> 5) * V7_WARP_SMEM;
+    u8* const stage0 = win + V7_WIN + 32;
     const unsigned lt_mask = (1u << lane) - 1u;
 
     for (;;) {
@@ -313,6 +317,17 @@ decompress_v7_kernel(const __grid_constant__ V7Params P)
         u32 cur = 0;
         bool bad = false;                  // an offset of this chunk points before its start (or is 0)
         u64 e_next = lane < ns ? tab[lane] : 0ull;
+        // stream positions below count from srcA, the stream start rounded down to 16 bytes (cp.async moves aligned blocks)
+        const u32 mis = (u32)(reinterpret_cast<uintptr_t>(src) & 15u);
+        const u8* const srcA = src - mis;
+        const u32 clenA = clen + mis;
+        u32 sb = 0, sbuf = 0;              // the staged bytes are positions [sb, sb + V7_STAGE) in buffer sbuf
+        {
+            u8* st = stage0;
+            if (lane * 16u < clenA) v7_cp16(st + lane * 16u, srcA + lane * 16u);
+            if (512u + lane * 16u < clenA) v7_cp16(st + 512u + lane * 16u, srcA + 512u + lane * 16u);
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        }
 
         while (cur < ns) {
             const bool valid = cur + lane < ns;
@@ -322,16 +337,30 @@ decompress_v7_kernel(const __grid_constant__ V7Params P)
             const u32 lsrc = (u32)(e >> 32) & 0xFFFFu;
             const u32 M = (u32)(e >> 48);
             const u32 opn = op + L + M;
+            // the literals and the offset of this lane: from the staged bytes if they are all there, else from global memory
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            __syncwarp();
+            const u32 lpos = lsrc + mis;
+            const bool staged = lpos >= sb && lpos + L + 2 <= sb + V7_STAGE;
+            const u8* const stg = stage0 + sbuf * V7_STAGE + (lpos - sb);
+            const u8* const lit = staged ? stg : srcA + lpos;           // generic pointer: shared or global
             u32 off = 0;
-            if (valid && M) off = (u32)__ldg(src + lsrc + L) | ((u32)__ldg(src + lsrc + L + 1) << 8);
+            if (valid && M) off = (u32)lit[L] | ((u32)lit[L + 1] << 8);
             const u32 op0 = __shfl_sync(FULL, op, 0);
             const bool lng = valid && (L > V7_CAP || M > V7_CAP);
             const unsigned stop = __ballot_sync(FULL, !valid || lng || opn - op0 > V7_SPAN);
             const u32 k = stop ? (u32)__ffs(stop) - 1u : 32u;          // lanes [0, k) form the group
             const bool lng_k = k < 32 && __shfl_sync(FULL, (u32)lng, k & 31);       // ... and a long sequence follows it
-            {   // the next group's entries: on their way while this one is executed
+            {   // the next group's entries and stream bytes: on their way while this one is executed
                 const u32 nx = cur + k + (lng_k ? 1u : 0u) + lane;
                 e_next = nx < ns ? tab[nx] : 0ull;
+                const u32 lastl = lng_k ? k : (k ? k - 1 : 0u);           // the stream continues behind this lane's literals
+                const u32 nsb = __shfl_sync(FULL, lpos + L, lastl) & ~15u;
+                sbuf ^= 1u; sb = nsb;
+                u8* st = stage0 + sbuf * V7_STAGE;
+                if (nsb + lane * 16u < clenA) v7_cp16(st + lane * 16u, srcA + nsb + lane * 16u);
+                if (nsb + 512u + lane * 16u < clenA) v7_cp16(st + 512u + lane * 16u, srcA + nsb + 512u + lane * 16u);
+                asm volatile("cp.async.commit_group;" ::: "memory");
             }
             // the offset rule (lz4/lz4.c:1764 checkOffset; offset 0 rejected as in the oracle): a bad one makes the chunk bad
             const bool off_bad = valid && M && (off == 0 || off > op - A + L);
@@ -356,13 +385,13 @@ decompress_v7_kernel(const __grid_constant__ V7Params P)
                     const u32 Lc = act ? L : 0u;
                     const u32 maxL = __reduce_max_sync(FULL, Lc);
                     u8* w = win + (op - win_base);
-                    const u8* s = src + lsrc;
+                    const u8* s = lit;
                     for (u32 i = 0; i < maxL; i += 4) {
                         u32 v0 = 0, v1 = 0, v2 = 0, v3 = 0;
-                        if (i + 0 < Lc) v0 = __ldg(s + i + 0);
-                        if (i + 1 < Lc) v1 = __ldg(s + i + 1);
-                        if (i + 2 < Lc) v2 = __ldg(s + i + 2);
-                        if (i + 3 < Lc) v3 = __ldg(s + i + 3);
+                        if (i + 0 < Lc) v0 = s[i + 0];
+                        if (i + 1 < Lc) v1 = s[i + 1];
+                        if (i + 2 < Lc) v2 = s[i + 2];
+                        if (i + 3 < Lc) v3 = s[i + 3];
                         if (i + 0 < Lc) w[i + 0] = (u8)v0;
                         if (i + 1 < Lc) w[i + 1] = (u8)v1;
                         if (i + 2 < Lc) w[i + 2] = (u8)v2;
@@ -505,7 +534,10 @@ inline cudaError_t v7_launch_parse(const V7Params& P, cudaStream_t st)
 inline cudaError_t v7_launch_decompress(const V7Params& P, int sm_count, cudaStream_t st)
 {
     int per_sm = 0;
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, decompress_v7_kernel, V7_WARPS * 32, 0);
+    const size_t smem = (size_t)V7_WARPS * V7_WARP_SMEM;
+    cudaError_t e = cudaFuncSetAttribute(decompress_v7_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   // per device: every launch
+    if (e != cudaSuccess) return e;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, decompress_v7_kernel, V7_WARPS * 32, smem);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) per_sm = 1;
     unsigned grid = (unsigned)(sm_count * per_sm);
@@ -513,7 +545,7 @@ inline cudaError_t v7_launch_decompress(const V7Params& P, int sm_count, cudaStr
     if (grid > need) grid = need;
     e = cudaMemsetAsync(P.ticket, 0, sizeof(u32), st);
     if (e != cudaSuccess) return e;
-    decompress_v7_kernel<<<grid, V7_WARPS * 32, 0, st>>>(P);
+    decompress_v7_kernel<<<grid, V7_WARPS * 32, smem, st>>>(P);
     return cudaGetLastError();
 }
 
