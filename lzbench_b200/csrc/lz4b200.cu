@@ -102,6 +102,9 @@ struct lz4b200_ctx {
     static constexpr int MAX_SLICES = 64;
     cudaStream_t streams[NS] = {};
     cudaStream_t d2h_stream = nullptr;
+    cudaStream_t aux_stream = nullptr;  // v7 decode: the team decoder's share of a large batch runs beside the sequence-table pass
+    cudaEvent_t ev_fork[MAX_SLICES] = {}, ev_join[MAX_SLICES] = {};
+    int split = -1;                     // percent of a large batch given to the team decoder (-1 = automatic, option "split")
     cudaStream_t h2d_stream = nullptr;  // ALL inbound bulk copies: spread over the compute streams they lose a third of the link (measured: 1 GiB each way in 32 ms on 8 streams, 22.6 ms on one)
     cudaEvent_t ev_sizes = nullptr, ev_scan[MAX_SLICES] = {}, ev_done[MAX_SLICES] = {}, ev_in[MAX_SLICES] = {};
     uint64_t launches = 0;
@@ -139,6 +142,7 @@ constexpr size_t SC_FBASE = 16;         // u64  frame container: position of the
 constexpr size_t SC_FUNSUP = 24;        // u32  frame container: blocks the size rule cannot represent
 constexpr size_t SC_FCK = 28;           // u32  frame container: block checksum mismatches
 constexpr size_t SC_TICKETS = 256;      // u32[MAX_SLICES] work tickets, one per slice
+constexpr size_t SC_TICKETS2 = 512;     // u32[MAX_SLICES] second ticket per slice (two decoders side by side)
 constexpr size_t SC_NJOBS = 1024;        // u64[MAX_SLICES] job counts of the segmented compressor, one per slice
 constexpr size_t SC_TEAMCOUNT = 2048;    // u32[MAX_SLICES] v7: chunks left to the team decoder, one counter per slice
 constexpr size_t SC_RUNNING = 4096;     // u64[MAX_SLICES] running compressed totals after each slice
@@ -149,6 +153,7 @@ struct Scratch {
     u64* uoff; u64* coff; u32* status; u8* stage; u32* ticket;
     u64* fsz;                          // frame mode only
     u64* v7_table; u64 v7_cap; u32 *v7_nseq, *v7_route, *v7_list, *v7_count;   // kernels_v7.cuh (null: not available)
+    u32* ticket2; int slice;
     size_t first_chunk;                // slices of one call own disjoint regions of the per-chunk / per-job arrays
 };
 
@@ -221,6 +226,8 @@ Scratch scratch_at(lz4b200_ctx* c, size_t first_chunk, size_t stride, int slice)
     s.status = (u32*)c->status.p + first_chunk;
     s.stage = c->stage.p ? (u8*)c->stage.p + first_chunk * stride : nullptr;   // `stride` = staging bytes per chunk
     s.ticket = (u32*)((u8*)c->scalars.p + SC_TICKETS) + slice;
+    s.ticket2 = (u32*)((u8*)c->scalars.p + SC_TICKETS2) + slice;
+    s.slice = slice;
     s.fsz = c->fsz.p ? (u64*)c->fsz.p + first_chunk : nullptr;
     s.v7_table = nullptr; s.v7_cap = 0; s.v7_nseq = s.v7_route = s.v7_list = s.v7_count = nullptr;
     if (c->v7_table.p && c->v7_chunks && first_chunk < c->v7_chunks) {
@@ -359,16 +366,39 @@ int decompress_slice(lz4b200_ctx* c, const u8* d_in, const u64* d_csz, const u64
         else team = n * 4 <= (size_t)c->sm_count * 32 ? 32 : (n * 2 <= (size_t)c->sm_count * 32 ? 16 : 8);
     }
     if (c->kernel_gen == 7 && s.v7_table && max_chunk <= V7_MAX_CHUNK) {
-        // sequence table, lane-per-sequence decoder, then the team decoder for the chunks left on the list
+        // sequence table, lane-per-sequence decoder, then the team decoder for the chunks left on the list.
+        // A large batch is cut in two: while the table of one part is being built -- a latency-bound pass that leaves the
+        // machine almost idle (one lane per chunk) -- the team decoder, whose run time is the latency of a chunk's chain
+        // rather than the number of chunks, works on the other part on a second stream.
         for (size_t b = 0; b < n; b += V7_SUB) {
             const size_t m = std::min(V7_SUB, n - b);
-            V7Params P{ d_in, s.coff + b, d_csz + b, s.uoff + b, d_usz + b, d_out, s.status + b, d_bad, s.ticket, (u32)m, cap_all,
-                        s.v7_table, s.v7_cap, s.v7_nseq + b, s.v7_route + b, s.v7_list + b, s.v7_count };
-            CU(v7_launch_parse(P, st));
-            CU(v7_launch_decompress(P, c->sm_count, st));
-            CU(v5_launch_decompress(team == 32 ? 16 : team, d_in, s.coff + b, d_csz + b, s.uoff + b, d_usz + b, d_out,
-                                    s.status + b, d_bad, (u32)m, s.ticket, c->sm_count, st, cap_all, s.v7_list + b, s.v7_count));
-            c->launches += 3;
+            const int pct = c->split >= 0 ? c->split : 0;       // measured: the table pass is a latency-bound chain, and ANY co-runner slows it (1 GiB: 4.1 ms alone, 6.0 ms at 20 %)
+            const size_t mA = (m >= 8192 && c->aux_stream) ? m * (size_t)pct / 100 : 0;   // team decoder's share: chunks [b, b + mA)
+            if (mA) {
+                if (!c->ev_fork[s.slice]) {
+                    CU(cudaEventCreateWithFlags(&c->ev_fork[s.slice], cudaEventDisableTiming));
+                    CU(cudaEventCreateWithFlags(&c->ev_join[s.slice], cudaEventDisableTiming));
+                }
+                CU(cudaEventRecord(c->ev_fork[s.slice], st));
+                CU(cudaStreamWaitEvent(c->aux_stream, c->ev_fork[s.slice], 0));
+            }
+            const size_t b2 = b + mA, m2 = m - mA;
+            if (m2) {
+                V7Params P{ d_in, s.coff + b2, d_csz + b2, s.uoff + b2, d_usz + b2, d_out, s.status + b2, d_bad, s.ticket, (u32)m2, cap_all,
+                            s.v7_table, s.v7_cap, s.v7_nseq + b2, s.v7_route + b2, s.v7_list + b2, s.v7_count };
+                CU(v7_launch_parse(P, st));
+                if (mA) {
+                    CU(v5_launch_decompress(16, d_in, s.coff + b, d_csz + b, s.uoff + b, d_usz + b, d_out, s.status + b, d_bad, (u32)mA,
+                                            s.ticket2, c->sm_count, c->aux_stream, cap_all));
+                    CU(cudaEventRecord(c->ev_join[s.slice], c->aux_stream));
+                    c->launches += 1;
+                }
+                CU(v7_launch_decompress(P, c->sm_count, st));
+                CU(v5_launch_decompress(team == 32 ? 16 : team, d_in, s.coff + b2, d_csz + b2, s.uoff + b2, d_usz + b2, d_out,
+                                        s.status + b2, d_bad, (u32)m2, s.ticket, c->sm_count, st, cap_all, s.v7_list + b2, s.v7_count));
+                c->launches += 3;
+            }
+            if (mA) CU(cudaStreamWaitEvent(st, c->ev_join[s.slice], 0));
         }
     } else if (c->kernel_gen >= 7) {
         CU(v5_launch_decompress(team == 32 ? 16 : team, d_in, s.coff, d_csz, s.uoff, d_usz, d_out, s.status, d_bad, (u32)n,
@@ -536,6 +566,9 @@ int lz4b200_create(int device, size_t max_total_bytes, size_t max_chunk_bytes, l
     if (cudaStreamCreateWithFlags(&c->h2d_stream, cudaStreamNonBlocking) != cudaSuccess) {
         lz4b200_destroy(c); return fail(-2, "cudaStreamCreate failed");
     }
+    if (cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking) != cudaSuccess) {
+        lz4b200_destroy(c); return fail(-2, "cudaStreamCreate failed");
+    }
     if (cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking) != cudaSuccess) {
         lz4b200_destroy(c); return fail(-2, "cudaStreamCreate failed");
     }
@@ -566,12 +599,15 @@ void lz4b200_destroy(lz4b200_ctx* c)
     for (int i = 0; i < c->n_regs; i++) cudaHostUnregister(const_cast<char*>(c->regs[i].p));
     for (int i = 0; i < lz4b200_ctx::NS; i++) if (c->streams[i]) cudaStreamDestroy(c->streams[i]);
     if (c->d2h_stream) cudaStreamDestroy(c->d2h_stream);
+    if (c->aux_stream) cudaStreamDestroy(c->aux_stream);
     if (c->h2d_stream) cudaStreamDestroy(c->h2d_stream);
     if (c->ev_sizes) cudaEventDestroy(c->ev_sizes);
     for (int i = 0; i < lz4b200_ctx::MAX_SLICES; i++) {
         if (c->ev_scan[i]) cudaEventDestroy(c->ev_scan[i]);
         if (c->ev_done[i]) cudaEventDestroy(c->ev_done[i]);
         if (c->ev_in[i]) cudaEventDestroy(c->ev_in[i]);
+        if (c->ev_fork[i]) cudaEventDestroy(c->ev_fork[i]);
+        if (c->ev_join[i]) cudaEventDestroy(c->ev_join[i]);
     }
     c->usz.release(); c->csz.release(); c->uoff.release(); c->coff.release();
     c->scalars.release(); c->status.release(); c->stage.release(); c->seg64.release(); c->seg32.release();
@@ -615,6 +651,10 @@ int lz4b200_set_option(lz4b200_ctx* c, const char* key, const char* value)
     if (!strcmp(key, "depth")) {                        // v6: iterations between fetching and storing a match part
         int d = atoi(value);
         if (d >= 2 && d <= 4) { v6_depth() = d; return 0; }
+    }
+    if (!strcmp(key, "split")) {                        // v7: percent of a large batch decoded by the team decoder beside the table pass (-1 = automatic)
+        int p = atoi(value);
+        if (p >= -1 && p <= 90) { c->split = p; return 0; }
     }
     if (!strcmp(key, "ramp")) { c->ramp = value[0] == '1'; return 0; }
     if (!strcmp(key, "h2d")) { c->own_h2d = strcmp(value, "shared") != 0; return 0; }

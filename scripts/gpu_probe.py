@@ -44,8 +44,10 @@ for kind in kinds:
     d_bad = torch.zeros(1, dtype=torch.int32, device="cuda")
     s = torch.cuda.current_stream().cuda_stream
     for gen in gens:
-        ctx.set_option("accel", "1")
-        if gen.startswith("c2a"):                       # c2a<acceleration>
+        ctx.set_option("accel", "1"); ctx.set_option("split", "-1")
+        if gen.startswith("v7s"):                        # v7s<percent of a large batch on the team decoder>
+            ctx.set_option("kernels", "v7"); ctx.set_option("split", gen[3:])
+        elif gen.startswith("c2a"):                       # c2a<acceleration>
             ctx.set_option("kernels", "v5"); ctx.set_option("compress", "v2"); ctx.set_option("accel", gen[3:])
         elif gen in ("c1", "c2"):
             ctx.set_option("kernels", "v4"); ctx.set_option("compress", "v" + gen[1])
