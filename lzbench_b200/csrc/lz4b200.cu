@@ -126,6 +126,7 @@ struct lz4b200_ctx {
     size_t v7_chunks = 0;               // chunk count the u32 arrays are laid out for (current call)
     size_t v7_table_chunks = 0;         // chunks the table has room for (current call): all of a host call's, one sub-batch of a device call's
     size_t v7_per_chunk = 0;            // table entries reserved per chunk (current call)
+    size_t v7_min_chunk = 32769;        // v7 only pays on chunks above 32 KiB (1 GiB mixed: 4 KiB 143 vs 356 GB/s, 32 KiB 238 vs 260, 64 KiB 262 vs 236); "kernels=v7" forces it
     // buffers behind the host entry points
     DevBuf d_plain, d_packed;
     PinBuf h_sizes;                     // u64[2*n_chunks + MAX_SLICES + 2]
@@ -211,7 +212,7 @@ constexpr size_t V7_SUB = 16384;            // chunks per sub-batch of a device-
 void ensure_v7(lz4b200_ctx* c, size_t n, size_t table_chunks, size_t max_chunk)
 {
     c->v7_chunks = c->v7_table_chunks = 0;
-    if (c->kernel_gen != 7 || max_chunk > V7_MAX_CHUNK || n == 0) return;
+    if (c->kernel_gen != 7 || max_chunk > V7_MAX_CHUNK || max_chunk < c->v7_min_chunk || n == 0) return;
     c->v7_per_chunk = (size_t)v7_entries_for(max_chunk, 1) + 2;      // + 2: the floors of a ragged prefix sum
     if (c->v7_u32.ensure(3 * n * sizeof(u32)) != cudaSuccess ||
         c->v7_table.ensure(table_chunks * c->v7_per_chunk * sizeof(u64)) != cudaSuccess) { cudaGetLastError(); return; }
@@ -631,7 +632,10 @@ int lz4b200_set_option(lz4b200_ctx* c, const char* key, const char* value)
         if (!strcmp(value, "v4")) { c->kernel_gen = 4; c->compress_gen = 2; return 0; }
         if (!strcmp(value, "v5")) { c->kernel_gen = 5; c->compress_gen = 2; return 0; }
         if (!strcmp(value, "v6")) { c->kernel_gen = 6; c->compress_gen = 2; return 0; }
-        if (!strcmp(value, "v7") || !strcmp(value, "default")) { c->kernel_gen = 7; c->compress_gen = 2; return 0; }
+        if (!strcmp(value, "v7") || !strcmp(value, "default")) {
+            c->kernel_gen = 7; c->compress_gen = 2; c->v7_min_chunk = strcmp(value, "v7") ? 32769 : 0;
+            return 0;
+        }
     }
     if (!strcmp(key, "compress")) {
         if (!strcmp(value, "v0")) { c->compress_gen = 0; return 0; }
