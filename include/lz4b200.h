@@ -78,7 +78,12 @@ int64_t lz4b200_decompress_batch(lz4b200_ctx* ctx, const char* in, const size_t*
 
 /* All pointers are device pointers on the context's device; `stream` is a cudaStream_t
  * (0 = default stream).  Size arrays are uint64_t.  Calls are asynchronous on `stream`.
- * d_total_out receives the total compressed size.  Returns 0 on successful launch. */
+ * d_total_out receives the total compressed size.  Returns 0 on successful launch.
+ * d_out must hold lz4b200_compress_device_bound(n_chunks, max_chunk_bytes) bytes: there is no capacity argument
+ * and a smaller buffer is overrun on the device.  The device entry points share per-context scratch
+ * (offsets, status, tickets, sequence table): calls on one context must be ordered -- issue them on the same
+ * stream, or synchronize `stream` before the next call (device or host entry point) on that context. */
+size_t lz4b200_compress_device_bound(size_t n_chunks, size_t max_chunk_bytes);
 int lz4b200_compress_device(lz4b200_ctx* ctx, const void* d_in, const uint64_t* d_chunk_sizes,
                             size_t n_chunks, size_t max_chunk_bytes, void* d_out,
                             uint64_t* d_compr_sizes, uint64_t* d_total_out, void* stream);
@@ -108,16 +113,25 @@ int lz4b200_debug_prof(lz4b200_ctx* ctx, uint64_t* out16);
  *              "v2" sub-warp teams; "v3" + every output byte owned by a fixed lane, match store pipelined behind its load;
  *              "v4" + warp-uniform predicated fast path; "v5" (default) + compressed stream through a cp.async shared-memory
  *              ring, long literal runs on the fast path, slow path out of line; "v6" experiment: v5 with the pending match
- *              bytes staged by cp.async ("depth" = "2".."4" iterations in flight).  Also sets the matching compressor.
+ *              bytes staged by cp.async ("depth" = "2".."4" iterations in flight); "v7": sequence table by one lane per
+ *              chunk, then one lane per sequence (kernels_v7.cuh), forced for every chunk size up to 64 KiB; "default":
+ *              v7 for chunks above 32 KiB up to 64 KiB, v5 otherwise.  Also sets the matching compressor.
+ *              The environment variable LZ4B200_KERNELS, read at lz4b200_create, is the same option.
  *   "team"     lanes per chunk for the team decoders: "4" / "8" / "16" / "32", "0" = by batch size (default)
  *   "compress" compressor generation: "v0" warp per chunk, "v1" one CTA per chunk, "v2" (default) two warp groups per CTA
  *   "accel"    LZ4_compress_fast's acceleration (lz4/lz4.c:1352-1375; the lz4fast levels of lzbench,
  *              _lzbench/compressors.cpp:348-356): 1 default, 2-3 probe every 2nd position, >= 4 every 4th
  *   "slices"   pipeline slices of the host entry points (0 = automatic); "ramp" = "0"/"1" small first slices when
  *              decompressing (default 1); "h2d" = "own"/"shared" stream for the inbound copies (default own)
- *   "host_register" = "1" page-locks caller buffers on first sight (what the lzbench wrappers turn on)
+ *   "host_register" = "1" page-locks caller buffers on first sight (what the lzbench wrappers turn on); a registered
+ *              buffer must outlive the context or be released with lz4b200_unregister_host before it is freed
+ *   "split"    v7: percent of a large batch decoded by the team decoder on a second stream ("0" default; measured slower)
  *   "timing" = "0"/"1" (see lz4b200_kernel_times_ms), "prof" = "0"/"1" (see lz4b200_debug_prof), "c1mode" (match-finder variant) */
 int lz4b200_set_option(lz4b200_ctx* ctx, const char* key, const char* value);
+
+/* Releases the page-lock that "host_register" put on the caller buffer containing `p` (0 = released, -1 = none
+ * found).  The context keeps up to 16 registrations and drops the oldest when a 17th buffer comes along. */
+int lz4b200_unregister_host(lz4b200_ctx* ctx, const void* p);
 
 /* ---- lzbench plugin-signature wrappers (drop-in comp_desc[] row "lz4_b200") -------------- */
 

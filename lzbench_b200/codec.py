@@ -55,6 +55,10 @@ def _load() -> C.CDLL:
     L.lz4b200_debug_prof.argtypes = [vp, vp]
     L.lz4b200_set_option.restype = C.c_int
     L.lz4b200_set_option.argtypes = [vp, C.c_char_p, C.c_char_p]
+    L.lz4b200_unregister_host.restype = C.c_int
+    L.lz4b200_unregister_host.argtypes = [vp, vp]
+    L.lz4b200_compress_device_bound.restype = sz
+    L.lz4b200_compress_device_bound.argtypes = [sz, sz]
     L.lzbench_lz4_b200_init.restype = vp
     L.lzbench_lz4_b200_init.argtypes = [sz, sz, sz]
     L.lzbench_lz4_b200_deinit.restype = None

@@ -415,12 +415,11 @@ template <int MODE>
 inline cudaError_t c1_launch_mode(const u8* in, const u64* in_off, const u64* usz, u8* stage, u64 stride, u64* csz,
                                       u32 n, u32* ticket, u64* prof, int sm_count, size_t, cudaStream_t st)
 {
-    static bool attr = false;
-    if (!attr) {
+    // the opt-in is per device (a process may hold contexts on several GPUs): set it at every launch, it is cheap
+    {
         cudaError_t e = cudaFuncSetAttribute(compress_c1_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)C1Smem::BYTES);
         if (e != cudaSuccess) return e;
-        attr = true;
     }
     unsigned grid = (unsigned)(sm_count * 2);
     if (grid > n) grid = n;
@@ -430,12 +429,11 @@ inline cudaError_t c1_launch_mode(const u8* in, const u64* in_off, const u64* us
     return cudaGetLastError();
 }
 
-inline int& c1_mode() { static int m = 2; return m; }   // intra-warp candidates: 0 match_any, 1 shuffle distances, 2 none (default: the batch-local table covers them)
-
+// mode = intra-warp candidates: 0 match_any, 1 shuffle distances, 2 none (default: the batch-local table covers them); a per-context option
 inline cudaError_t c1_launch_compress(const u8* in, const u64* in_off, const u64* usz, u8* stage, u64 stride, u64* csz,
-                                      u32 n, u32* ticket, u64* prof, int sm_count, size_t mc, cudaStream_t st)
+                                      u32 n, u32* ticket, u64* prof, int sm_count, size_t mc, cudaStream_t st, int mode = 2)
 {
-    switch (c1_mode()) {
+    switch (mode) {
     case 1:  return c1_launch_mode<1>(in, in_off, usz, stage, stride, csz, n, ticket, prof, sm_count, mc, st);
     case 2:  return c1_launch_mode<2>(in, in_off, usz, stage, stride, csz, n, ticket, prof, sm_count, mc, st);
     default: return c1_launch_mode<0>(in, in_off, usz, stage, stride, csz, n, ticket, prof, sm_count, mc, st);

@@ -462,12 +462,11 @@ template <int MODE, int ACC>
 inline cudaError_t c2_launch_mode(const u8* in, const u64* in_off, const u64* usz, u8* stage, u64 stride, u64* csz,
                                   u32 n, u32* ticket, int sm_count, cudaStream_t st, const u64* n_dev, u32* tail_pos, u32* tail_len, const u32* hist, u64* prof)
 {
-    static bool attr = false;
-    if (!attr) {
+    // the opt-in is per device (a process may hold contexts on several GPUs): set it at every launch, it is cheap
+    {
         cudaError_t e = cudaFuncSetAttribute(compress_c2_kernel<MODE, ACC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)C2Smem::BYTES);
         if (e != cudaSuccess) return e;
-        attr = true;
     }
     unsigned grid = (unsigned)(sm_count * 2);
     if (grid > n) grid = n;
@@ -480,14 +479,14 @@ inline cudaError_t c2_launch_mode(const u8* in, const u64* in_off, const u64* us
 inline cudaError_t c2_launch_compress(const u8* in, const u64* in_off, const u64* usz, u8* stage, u64 stride, u64* csz,
                                       u32 n, u32* ticket, int sm_count, cudaStream_t st, const u64* n_dev = nullptr,
                                       u32* tail_pos = nullptr, u32* tail_len = nullptr, const u32* hist = nullptr, u64* prof = nullptr,
-                                      u32 accel = 1)
+                                      u32 accel = 1, int mode = 2)
 {
     // acceleration (lz4fast levels): probe grid of 2 (accel 2-3) or 4 (accel >= 4) positions.  A grid of 8 was measured:
     // 133 GB/s but 6.8 % larger than the reference at accel 8, while the grid of 4 is SMALLER than the reference from
     // accel 8 on (66.0 % vs 70.4 %) at 127 GB/s.  The match-finding modes 0 / 1 exist only at acceleration 1.
     if (accel >= 4) return c2_launch_mode<2, 4>(in, in_off, usz, stage, stride, csz, n, ticket, sm_count, st, n_dev, tail_pos, tail_len, hist, prof);
     if (accel >= 2) return c2_launch_mode<2, 2>(in, in_off, usz, stage, stride, csz, n, ticket, sm_count, st, n_dev, tail_pos, tail_len, hist, prof);
-    switch (c1_mode()) {
+    switch (mode) {
     case 0:  return c2_launch_mode<0, 1>(in, in_off, usz, stage, stride, csz, n, ticket, sm_count, st, n_dev, tail_pos, tail_len, hist, prof);
     case 2:  return c2_launch_mode<2, 1>(in, in_off, usz, stage, stride, csz, n, ticket, sm_count, st, n_dev, tail_pos, tail_len, hist, prof);
     default: return c2_launch_mode<1, 1>(in, in_off, usz, stage, stride, csz, n, ticket, sm_count, st, n_dev, tail_pos, tail_len, hist, prof);

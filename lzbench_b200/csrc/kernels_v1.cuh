@@ -526,11 +526,10 @@ inline cudaError_t d1_launch(const u8* in, const u64* in_off, const u64* csz, co
 {
     using Cfg = D1Cfg<CHUNK_MAX, THREADS, WS_MIN>;
     auto kern = decompress_v1_kernel<CHUNK_MAX, THREADS, WS_MIN>;
-    static bool attr = false;
-    if (!attr) {
+    // the opt-in is per device (a process may hold contexts on several GPUs): set it at every launch, it is cheap
+    {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES);
         if (e != cudaSuccess) return e;
-        attr = true;
     }
     int per_sm = (int)(227u * 1024u / (Cfg::SMEM_BYTES + 1024u));
     if (per_sm < 1) per_sm = 1;

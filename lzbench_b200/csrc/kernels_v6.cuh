@@ -210,13 +210,10 @@ inline cudaError_t v6_launch_t(const u8* in, const u64* in_off, const u64* csz, 
     return cudaGetLastError();
 }
 
-inline int& v6_depth() { static int d = 2; return d; }
-
 inline cudaError_t v6_launch_decompress(int team, const u8* in, const u64* in_off, const u64* csz, const u64* out_off,
                                         const u64* usz, u8* out, u32* status, u32* bad, u32 n, u32* ticket,
-                                        int sm_count, cudaStream_t st)
+                                        int sm_count, cudaStream_t st, int d = 2)
 {
-    const int d = v6_depth();
     if (team == 4) {
         // depth <= 3 on 4-lane teams: a ring segment (64 bytes here) is requested two segments ahead and must have landed
         // >= 3 iterations later, which wait_group 3 would not guarantee

@@ -88,6 +88,8 @@ struct lz4b200_ctx {
     int sm_count = 148;
     int kernel_gen = 7;                 // decode: 7 = sequence table + one lane per sequence (kernels_v7.cuh; default for chunks <= 64 KiB, v5 otherwise and for the chunks v7 leaves to it); 0 warp per chunk, 1 CTA tile (TMA), 2 sub-warp teams, 3 + mapped lanes / pipelined match, 4 + warp-uniform fast path, 5 + compressed stream through a cp.async ring, long literal runs on the common path (default), 6 = 5 with cp.async-staged deep match pipeline (experiment)
     int compress_gen = 2;               // compress: 0 warp per chunk, 1 CTA per chunk (parallel match finder + speculative parse), 2 = 1 with the phases on two warp groups (default)
+    int c1mode = 2;                     // compress: intra-warp candidate mode of the match finder (experiments; see kernels_c1.cuh)
+    int v6depth = 2;                    // decode v6: iterations between fetching and storing a match part
     int accel = 1;                      // compress: LZ4_compress_fast's acceleration (1 = lz4 default; lz4fast levels), probe grid 1/2/4/8
     int team = 0;                       // lanes per chunk for the team decoders: 8 / 16 / 32, 0 = by batch size
     int slices = 0;                     // host entry points: number of pipeline slices (0 = automatic)
@@ -208,7 +210,7 @@ int ensure_scratch(lz4b200_ctx* c, size_t n, size_t stage_bytes)
 
 // v7 decode scratch: u32 arrays for n chunks, table room for table_chunks chunks of at most max_chunk bytes.  Failing to
 // get the memory is not an error: the slice then runs on the team decoder.
-constexpr size_t V7_SUB = 16384;            // chunks per sub-batch of a device-resident call (bounds the table: 2 x their bytes)
+constexpr size_t V7_SUB = 65536;            // chunks per sub-batch of a device-resident call (bounds the table: 2 x their bytes)
 void ensure_v7(lz4b200_ctx* c, size_t n, size_t table_chunks, size_t max_chunk)
 {
     c->v7_chunks = c->v7_table_chunks = 0;
@@ -286,24 +288,20 @@ int compress_slice(lz4b200_ctx* c, const u8* d_in, const u64* d_usz, size_t n, s
         seg_fill_kernel<<<gb, 256, 0, st>>>(d_usz, s.uoff, sa, (u32)n);
         CU(c2_launch_compress(d_in, sa.job_in_off, sa.job_len, s.stage, slot_stride_for(SEG_BYTES), sa.job_csz,
                               (u32)jobs_max, s.ticket, c->sm_count, st, sa.n_jobs, sa.job_tail_pos, sa.job_tail_len, sa.job_hist, nullptr,
-                              (u32)c->accel));
+                              (u32)c->accel, c->c1mode));
         seg_stitch_size_kernel<<<gb, 256, 0, st>>>(sa, s.stage, slot_stride_for(SEG_BYTES), d_csz, (u32)n);
         c->launches += 5;
     } else if (c->compress_gen == 2 && c1_compress_supported(max_chunk)) {
         CU(c2_launch_compress(d_in, s.uoff, d_usz, s.stage, stride, d_csz, (u32)n, s.ticket, c->sm_count, st, nullptr, nullptr, nullptr,
-                              nullptr, c->prof_on ? (u64*)c->prof.p : nullptr, (u32)c->accel));
+                              nullptr, c->prof_on ? (u64*)c->prof.p : nullptr, (u32)c->accel, c->c1mode));
         c->launches++;
     } else if (c->compress_gen == 1 && c1_compress_supported(max_chunk)) {
         CU(c1_launch_compress(d_in, s.uoff, d_usz, s.stage, stride, d_csz, (u32)n, s.ticket,
-                              c->prof_on ? (u64*)c->prof.p : nullptr, c->sm_count, max_chunk, st));
+                              c->prof_on ? (u64*)c->prof.p : nullptr, c->sm_count, max_chunk, st, c->c1mode));
         c->launches++;
     } else {
         const size_t smem = (size_t)V0_WARPS * V0_TABLE * sizeof(u16);
-        static bool attr_set = false;
-        if (!attr_set) {
-            CU(cudaFuncSetAttribute(compress_v0_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            attr_set = true;
-        }
+        CU(cudaFuncSetAttribute(compress_v0_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   // per device: every launch
         compress_v0_kernel<<<(unsigned)((n + V0_WARPS - 1) / V0_WARPS), V0_WARPS * 32, smem, st>>>(
             d_in, s.uoff, d_usz, s.stage, stride, d_csz, (u32)n);
         c->launches++;
@@ -407,7 +405,7 @@ int decompress_slice(lz4b200_ctx* c, const u8* d_in, const u64* d_csz, const u64
         c->launches += 1;
     } else if (c->kernel_gen == 6 && team != 32) {
         CU(v6_launch_decompress(team, d_in, s.coff, d_csz, s.uoff, d_usz, d_out, s.status, d_bad, (u32)n,
-                                s.ticket, c->sm_count, st));
+                                s.ticket, c->sm_count, st, c->v6depth));
         c->launches += 1;
     } else if (c->kernel_gen == 5 && team != 32) {
         CU(v5_launch_decompress(team, d_in, s.coff, d_csz, s.uoff, d_usz, d_out, s.status, d_bad, (u32)n,
@@ -450,7 +448,11 @@ void maybe_register(lz4b200_ctx* c, const char* p, size_t n)
     if (!c->host_register || n < (1u << 20)) return;
     for (int i = 0; i < c->n_regs; i++)
         if (p >= c->regs[i].p && p + n <= c->regs[i].p + c->regs[i].n) return;
-    if (c->n_regs == 16) return;
+    if (c->n_regs == 16) {                               // drop the oldest registration
+        cudaHostUnregister(const_cast<char*>(c->regs[0].p)); cudaGetLastError();
+        for (int i = 1; i < 16; i++) c->regs[i - 1] = c->regs[i];
+        c->n_regs = 15;
+    }
     cudaPointerAttributes attr;
     if (cudaPointerGetAttributes(&attr, p) == cudaSuccess && attr.type != cudaMemoryTypeUnregistered) return;
     cudaGetLastError();
@@ -546,20 +548,12 @@ int lz4b200_create(int device, size_t max_total_bytes, size_t max_chunk_bytes, l
     CU(cudaSetDevice(device));
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, device));
-    if (prop.major < 10) return fail(-2, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+    if (prop.major != 10 || prop.minor != 0) return fail(-2, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
     lz4b200_ctx* c = new (std::nothrow) lz4b200_ctx();
     if (!c) return fail(-3, "out of host memory");
     c->device = device;
     c->sm_count = prop.multiProcessorCount;
-    const char* gen = getenv("LZ4B200_KERNELS");
-    if (gen && !strcmp(gen, "v0")) { c->kernel_gen = 0; c->compress_gen = 0; }
-    if (gen && !strcmp(gen, "v1")) c->kernel_gen = 1;
-    if (gen && !strcmp(gen, "v2")) c->kernel_gen = 2;
-    if (gen && !strcmp(gen, "v3")) c->kernel_gen = 3;
-    if (gen && !strcmp(gen, "v4")) c->kernel_gen = 4;
-    if (gen && !strcmp(gen, "v5")) c->kernel_gen = 5;
-    if (gen && !strcmp(gen, "v6")) c->kernel_gen = 6;
-    if (gen && !strcmp(gen, "v7")) c->kernel_gen = 7;
+    if (const char* gen = getenv("LZ4B200_KERNELS")) lz4b200_set_option(c, "kernels", gen);   // same meaning as the option
     for (int i = 0; i < lz4b200_ctx::NS; i++) {
         cudaError_t e = cudaStreamCreateWithFlags(&c->streams[i], cudaStreamNonBlocking);
         if (e != cudaSuccess) { lz4b200_destroy(c); return fail(-2, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
@@ -582,6 +576,7 @@ int lz4b200_create(int device, size_t max_total_bytes, size_t max_chunk_bytes, l
         c->usz.ensure(n * 8); c->csz.ensure(n * 8); c->uoff.ensure(n * 8); c->coff.ensure(n * 8);
         c->status.ensure(n * 4);
         c->h_sizes.ensure((2 * n + lz4b200_ctx::MAX_SLICES + 2) * 8);
+        cudaGetLastError();                              // best effort: a failed allocation here must not surface at the first launch
     }
     if (ensure_scratch(c, 1, 0) != 0) { lz4b200_destroy(c); return -2; }
     if (cudaHostAlloc((void**)&c->h_mirror, lz4b200_ctx::MAX_SLICES * sizeof(u64), cudaHostAllocMapped) != cudaSuccess ||
@@ -621,6 +616,30 @@ void lz4b200_destroy(lz4b200_ctx* c)
 
 uint64_t lz4b200_launch_count(const lz4b200_ctx* c) { return c ? c->launches : 0; }
 
+size_t lz4b200_compress_device_bound(size_t n_chunks, size_t max_chunk)
+{
+    // compact image: every chunk at most its bound; the segmented path (chunks > 64 KiB) adds up to 16 bytes per 48 KiB segment
+    const size_t b = lz4b200_compress_bound(max_chunk);
+    if (!b) return 0;
+    return n_chunks * (b + 16 * (max_chunk / SEG_NEW + 2)) + 16;
+}
+
+int lz4b200_unregister_host(lz4b200_ctx* c, const void* p)
+{
+    if (!c || !p) return -1;
+    for (int i = 0; i < c->n_regs; i++) {
+        const char* q = (const char*)p;
+        if (q >= c->regs[i].p && q < c->regs[i].p + c->regs[i].n) {
+            cudaSetDevice(c->device);
+            cudaHostUnregister(const_cast<char*>(c->regs[i].p)); cudaGetLastError();
+            for (int j = i + 1; j < c->n_regs; j++) c->regs[j - 1] = c->regs[j];
+            c->n_regs--;
+            return 0;
+        }
+    }
+    return -1;
+}
+
 int lz4b200_set_option(lz4b200_ctx* c, const char* key, const char* value)
 {
     if (!c || !key || !value) return -1;
@@ -642,7 +661,7 @@ int lz4b200_set_option(lz4b200_ctx* c, const char* key, const char* value)
         if (!strcmp(value, "v1")) { c->compress_gen = 1; return 0; }
         if (!strcmp(value, "v2")) { c->compress_gen = 2; return 0; }
     }
-    if (!strcmp(key, "c1mode")) { c1_mode() = atoi(value); return 0; }
+    if (!strcmp(key, "c1mode")) { c->c1mode = atoi(value); return 0; }
     if (!strcmp(key, "accel")) {                        // LZ4_compress_fast's acceleration (lz4/lz4.c:1352-1375); the lz4fast levels of lzbench
         int a = atoi(value);
         c->accel = a < 1 ? 1 : (a > 65537 ? 65537 : a);
@@ -654,7 +673,7 @@ int lz4b200_set_option(lz4b200_ctx* c, const char* key, const char* value)
     }
     if (!strcmp(key, "depth")) {                        // v6: iterations between fetching and storing a match part
         int d = atoi(value);
-        if (d >= 2 && d <= 4) { v6_depth() = d; return 0; }
+        if (d >= 2 && d <= 4) { c->v6depth = d; return 0; }
     }
     if (!strcmp(key, "split")) {                        // v7: percent of a large batch decoded by the team decoder beside the table pass (-1 = automatic)
         int p = atoi(value);

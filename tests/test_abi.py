@@ -33,6 +33,13 @@ def test_compress_bound_matches_reference_macro():
     assert L.compress_bound(65536) == 65809
 
 
+def test_compress_device_bound_covers_every_chunk():
+    # device entry point without a capacity argument: the documented size covers n chunks at their bound (+ segment slack)
+    for n, mc in ((1, 1), (7, 4096), (16384, 65536), (3, 1 << 20), (2, 4 << 20)):
+        assert L.lib.lz4b200_compress_device_bound(n, mc) >= n * L.compress_bound(mc)
+    assert L.lib.lz4b200_compress_device_bound(1, 0x7E000001) == 0
+
+
 def test_chunk_list_matches_lzbench():
     # _lzbench/lzbench.cpp:366-373
     assert L.chunk_list(65536 * 3, 65536).tolist() == [65536] * 3

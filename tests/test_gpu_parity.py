@@ -412,3 +412,34 @@ def test_v7_unaligned_output_and_input(gpu_ctx):
         packed, compr = O.oracle_chunked_compress(data[:n], cs)
         out, r = gpu_ctx.decompress_batch(packed, compr, cs)
         assert r == n and np.array_equal(out, data[:n]), lead
+
+
+def test_contexts_on_two_devices_in_one_process():
+    """The shared-memory opt-in of the tiled kernels is per device: a second context on another GPU must work
+    (the driver runs one process per GPU; a host application may not)."""
+    if L.lib.lz4b200_device_count() < 2:
+        pytest.skip("one GPU visible")
+    data = L.corpus("mixed", 3 * 65536 + 5, seed=4)
+    cs = L.chunk_list(len(data), 65536)
+    for dev in (0, 1, 0):
+        with L.Lz4B200(dev) as ctx:
+            packed, compr, total = ctx.compress_batch(data, cs)
+            check_gpu_blocks_with_reference(data, packed[:total], compr, cs)
+            out, r = ctx.decompress_batch(packed[:total], compr, cs)
+            assert r == len(data) and np.array_equal(out, data)
+
+
+def test_registered_host_buffers_can_be_released(gpu_ctx):
+    """host_register page-locks caller buffers on first sight; lz4b200_unregister_host releases one before it is freed."""
+    data = L.corpus("mixed", 4 << 20, seed=5)
+    cs = L.chunk_list(len(data), 65536)
+    gpu_ctx.set_option("host_register", "1")
+    try:
+        packed, compr, total = gpu_ctx.compress_batch(data, cs)
+        assert total > 0
+        assert L.lib.lz4b200_unregister_host(gpu_ctx._h, data.ctypes.data) == 0
+        assert L.lib.lz4b200_unregister_host(gpu_ctx._h, data.ctypes.data) == -1
+        out, r = gpu_ctx.decompress_batch(packed[:total], compr, cs)
+        assert r == len(data) and np.array_equal(out, data)
+    finally:
+        gpu_ctx.set_option("host_register", "0")
