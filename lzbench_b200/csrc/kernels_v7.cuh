@@ -38,6 +38,7 @@ constexpr int V7_WARPS = 8;                // warps per CTA of the lane-per-sequ
 constexpr u32 V7_STAGE = 1024;             // stream bytes staged per group (two 16-byte blocks per lane)
 constexpr u32 V7_WARP_SMEM = 4096 + 32 + 2 * 1024;   // V7_WIN + 32 + 2 * V7_STAGE
 constexpr u32 V7_ROUTE_NONE = 0, V7_ROUTE_SEQ = 1, V7_ROUTE_TEAM = 2;
+constexpr u32 V7_BUCKETS = 64;             // chunks are ordered by sequence count / 128 (64 KiB chunks have up to ~8000)
 
 // entries of the table a chunk may need: sequences (>= 4 output bytes each but the last), literal pieces, terminator
 __host__ __device__ inline u64 v7_entries_for(u64 out_bytes, u64 chunks)
@@ -54,6 +55,7 @@ struct V7Params {
     u32* nseq;                             // entries per chunk (without the terminator)
     u32* route;                            // V7_ROUTE_* per chunk
     u32* team_list; u32* team_count;       // chunks left to the team decoder
+    u32* order; u32* bucket;               // pass 2 takes the chunks with the most sequences first: order[ticket], bucket counters u32[2][V7_BUCKETS]
 };
 
 // entry, low word: bits 0-16 output position of the sequence, 17-29 literal count; high word: bits 0-15 stream position
@@ -62,6 +64,22 @@ struct V7Params {
 __device__ __forceinline__ u64 v7_pack(u32 op, u32 lsrc, u32 M, u32 L)
 {
     return (u64)(op | (L << 17)) | ((u64)(lsrc | (M << 16)) << 32);
+}
+
+// chunks with more sequences take longer in pass 2; bucket 0 = nothing to do there
+__device__ __forceinline__ u32 v7_bucket(u32 nseq) { const u32 b = 1u + (nseq >> 7); return b < V7_BUCKETS ? b : V7_BUCKETS - 1; }
+
+// order[] = the chunks sorted by bucket, largest first (a warp of pass 2 works through ~5 chunks of ~0.5 ms each: with the
+// long ones first the last warps finish closer together)
+__global__ void __launch_bounds__(256)
+order_v7_kernel(const __grid_constant__ V7Params P)
+{
+    const u32 c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= P.n_chunks) return;
+    const u32 b = P.route[c] == V7_ROUTE_SEQ ? v7_bucket(P.nseq[c]) : 0u;
+    u32 base = 0;
+    for (u32 i = V7_BUCKETS - 1; i > b; i--) base += P.bucket[i];
+    P.order[base + atomicAdd(P.bucket + V7_BUCKETS + b, 1u)] = c;
 }
 
 // ---- pass 1: the token chain, one lane per chunk ---------------------------------------------------------------
@@ -250,6 +268,7 @@ parse_v7_kernel(const __grid_constant__ V7Params P)
     P.route[c] = route;
     if (err && P.bad_chunks) atomicAdd(P.bad_chunks, 1u);
     if (route == V7_ROUTE_TEAM) P.team_list[atomicAdd(P.team_count, 1u)] = c;
+    atomicAdd(P.bucket + (route == V7_ROUTE_SEQ ? v7_bucket(k) : 0u), 1u);
 }
 
 // ---- pass 2: one warp per chunk, one lane per sequence ----------------------------------------------------------
@@ -302,7 +321,8 @@ decompress_v7_kernel(const __grid_constant__ V7Params P)
         if (lane == 0) c = atomicAdd(P.ticket, 1u);
         c = __shfl_sync(FULL, c, 0);
         if (c >= P.n_chunks) break;
-        if (P.route[c] != V7_ROUTE_SEQ) continue;
+        c = P.order[c];
+        if (P.route[c] != V7_ROUTE_SEQ) break;                            // the rest of the order is not for this kernel
         const u8* __restrict__ src = P.in + P.in_off[c];
         u8* const dst = P.out + P.out_off[c];
         const u32 clen = (u32)P.csz[c], n = (u32)P.usz[c];
@@ -527,7 +547,10 @@ inline cudaError_t v7_launch_parse(const V7Params& P, cudaStream_t st)
 {
     cudaError_t e = cudaMemsetAsync(P.team_count, 0, sizeof(u32), st);
     if (e != cudaSuccess) return e;
+    e = cudaMemsetAsync(P.bucket, 0, 2 * V7_BUCKETS * sizeof(u32), st);
+    if (e != cudaSuccess) return e;
     parse_v7_kernel<<<(P.n_chunks + 31) / 32, 32, 0, st>>>(P);
+    order_v7_kernel<<<(P.n_chunks + 255) / 256, 256, 0, st>>>(P);
     return cudaGetLastError();
 }
 

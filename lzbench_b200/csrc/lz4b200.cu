@@ -155,7 +155,7 @@ constexpr size_t SC_BYTES = 8192;
 struct Scratch {
     u64* uoff; u64* coff; u32* status; u8* stage; u32* ticket;
     u64* fsz;                          // frame mode only
-    u64* v7_table; u64 v7_cap; u32 *v7_nseq, *v7_route, *v7_list, *v7_count;   // kernels_v7.cuh (null: not available)
+    u64* v7_table; u64 v7_cap; u32 *v7_nseq, *v7_route, *v7_list, *v7_count, *v7_order, *v7_bucket;   // kernels_v7.cuh (null: not available)
     u32* ticket2; int slice;
     size_t first_chunk;                // slices of one call own disjoint regions of the per-chunk / per-job arrays
 };
@@ -216,7 +216,7 @@ void ensure_v7(lz4b200_ctx* c, size_t n, size_t table_chunks, size_t max_chunk)
     c->v7_chunks = c->v7_table_chunks = 0;
     if (c->kernel_gen != 7 || max_chunk > V7_MAX_CHUNK || max_chunk < c->v7_min_chunk || n == 0) return;
     c->v7_per_chunk = (size_t)v7_entries_for(max_chunk, 1) + 2;      // + 2: the floors of a ragged prefix sum
-    if (c->v7_u32.ensure(3 * n * sizeof(u32)) != cudaSuccess ||
+    if (c->v7_u32.ensure((4 * n + 2 * V7_BUCKETS * lz4b200_ctx::MAX_SLICES) * sizeof(u32)) != cudaSuccess ||
         c->v7_table.ensure(table_chunks * c->v7_per_chunk * sizeof(u64)) != cudaSuccess) { cudaGetLastError(); return; }
     c->v7_chunks = n; c->v7_table_chunks = table_chunks;
 }
@@ -232,7 +232,7 @@ Scratch scratch_at(lz4b200_ctx* c, size_t first_chunk, size_t stride, int slice)
     s.ticket2 = (u32*)((u8*)c->scalars.p + SC_TICKETS2) + slice;
     s.slice = slice;
     s.fsz = c->fsz.p ? (u64*)c->fsz.p + first_chunk : nullptr;
-    s.v7_table = nullptr; s.v7_cap = 0; s.v7_nseq = s.v7_route = s.v7_list = s.v7_count = nullptr;
+    s.v7_table = nullptr; s.v7_cap = 0; s.v7_nseq = s.v7_route = s.v7_list = s.v7_count = s.v7_order = s.v7_bucket = nullptr;
     if (c->v7_table.p && c->v7_chunks && first_chunk < c->v7_chunks) {
         // every slice owns the table region of its chunks (slices of one host call run concurrently)
         if (first_chunk < c->v7_table_chunks) {
@@ -241,6 +241,7 @@ Scratch scratch_at(lz4b200_ctx* c, size_t first_chunk, size_t stride, int slice)
         }
         u32* b = (u32*)c->v7_u32.p;
         s.v7_nseq = b + first_chunk; s.v7_route = b + c->v7_chunks + first_chunk; s.v7_list = b + 2 * c->v7_chunks + first_chunk;
+        s.v7_order = b + 3 * c->v7_chunks + first_chunk; s.v7_bucket = b + 4 * c->v7_chunks + 2 * V7_BUCKETS * slice;
         s.v7_count = (u32*)((u8*)c->scalars.p + SC_TEAMCOUNT) + slice;
     }
     s.first_chunk = first_chunk;
@@ -384,7 +385,7 @@ int decompress_slice(lz4b200_ctx* c, const u8* d_in, const u64* d_csz, const u64
             const size_t b2 = b + mA, m2 = m - mA;
             if (m2) {
                 V7Params P{ d_in, s.coff + b2, d_csz + b2, s.uoff + b2, d_usz + b2, d_out, s.status + b2, d_bad, s.ticket, (u32)m2, cap_all,
-                            s.v7_table, s.v7_cap, s.v7_nseq + b2, s.v7_route + b2, s.v7_list + b2, s.v7_count };
+                            s.v7_table, s.v7_cap, s.v7_nseq + b2, s.v7_route + b2, s.v7_list + b2, s.v7_count, s.v7_order + b2, s.v7_bucket };
                 CU(v7_launch_parse(P, st));
                 if (mA) {
                     CU(v5_launch_decompress(16, d_in, s.coff + b, d_csz + b, s.uoff + b, d_usz + b, d_out, s.status + b, d_bad, (u32)mA,
@@ -395,7 +396,7 @@ int decompress_slice(lz4b200_ctx* c, const u8* d_in, const u64* d_csz, const u64
                 CU(v7_launch_decompress(P, c->sm_count, st));
                 CU(v5_launch_decompress(team == 32 ? 16 : team, d_in, s.coff + b2, d_csz + b2, s.uoff + b2, d_usz + b2, d_out,
                                         s.status + b2, d_bad, (u32)m2, s.ticket, c->sm_count, st, cap_all, s.v7_list + b2, s.v7_count));
-                c->launches += 3;
+                c->launches += 4;
             }
             if (mA) CU(cudaStreamWaitEvent(st, c->ev_join[s.slice], 0));
         }
