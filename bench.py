@@ -9,7 +9,9 @@ reported in the same JSON line under "compress" -- one compression pass of the s
              MB = 1e6, _lzbench/lzbench.cpp:104-105), all ranks' bytes / max-over-ranks time
   e2e        same metric through the reference-facing C-ABI call lz4b200_decompress_batch with pinned
              HOST buffers: H2D of the compressed image + size tables and D2H of the result inside
-  roofline   (U + C) bytes per launch of the codec kernel / its CUDA-event duration, vs measured HBM peak
+  roofline   (U + C) bytes per launch of the codec pass / its CUDA-event duration, vs measured HBM peak (decode is
+             three kernels since round 2 -- sequence table, order, lane-per-sequence decoder -- timed as ONE event pair:
+             the fraction is that of the whole pass, not of its fastest kernel)
   cpu_baseline  the reference's own lz4 1.9.3 (oracle/_ref, compiled from the reference tree) driven by
              lzbench's chunk loop on the host cores, bounded sample
 
@@ -354,7 +356,7 @@ def run_b200(args):
     # dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full captures under profiles/
     # (profiles/README.md), valid for the default workload only (1 GiB mixed, 64 KiB chunks, default kernels)
     default_cfg = args.size_mib == 1024 and chunk == 65536 and args.corpus == "mixed" and not args.kernels
-    traffic = {"decompress": 3.4254e9 if default_cfg else None,          # profiles/r01_final_decompress_v5_ncu_raw.csv
+    traffic = {"decompress": 3.4989e9 if default_cfg else None,          # profiles/r02_decompress_v7_ncu_raw.csv: table pass 0.41 + 0.48, lane-per-sequence pass 1.57 + 1.03 GB
                "compress": 1.6951e9 if default_cfg else None}            # profiles/r01_final_compress_c2_ncu_raw.csv
 
     def roof(kt, which):
@@ -364,7 +366,9 @@ def run_b200(args):
         ach = (U + Cb) / t / GB
         return {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                 "traffic": traffic[which], "kernel_ms": t * 1e3, "launches_timed": len(kt), "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": U + Cb}
+                "algorithmic_bytes_per_launch": U + Cb,
+                "timed": ("parse_v7_kernel + order_v7_kernel + decompress_v7_kernel + decompress_v5_kernel (work list, empty here), one event pair"
+                          if which == "decompress" and not args.kernels and chunk > 32768 and chunk <= 65536 else "the codec kernel of the pass")}
 
     line = {
         "metric": "lz4_block_decompress_GBps_uncompressed",

@@ -23,7 +23,11 @@ for l in lines[start:end]:
         seq.append(cur)
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--print-source", "sass", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(out)))
-hdr, data = rows[1], rows[2:]
+# a report may hold several kernels: every one starts with a "Kernel Name" row followed by the column header
+starts = [i for i, r in enumerate(rows) if r and r[0] == "Kernel Name"]
+pick = next(i for i in starts if sym in rows[i][1])
+stop = next((i for i in starts if i > pick), len(rows))
+hdr, data = rows[pick + 1], [r for r in rows[pick + 2:stop] if r]
 ia, ismp = hdr.index("Instructions Executed"), hdr.index("# Samples")
 assert len(seq) == len(data), (len(seq), len(data), "the report is from another build")
 by = collections.defaultdict(lambda: [0, 0])
