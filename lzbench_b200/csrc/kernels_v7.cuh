@@ -35,8 +35,8 @@ constexpr u32 V7_KEEP = 1008;              // history kept below a group when th
 constexpr u32 V7_LPIECE = 8191;            // literal runs are cut into entries of at most this many bytes (13-bit field)
 constexpr u32 V7_MAX_CHUNK = 65536;
 constexpr int V7_WARPS = 8;                // warps per CTA of the lane-per-sequence kernel
-constexpr u32 V7_STAGE = 1024;             // stream bytes staged per group (two 16-byte blocks per lane)
-constexpr u32 V7_WARP_SMEM = 4096 + 32 + 2 * 1024;   // V7_WIN + 32 + 2 * V7_STAGE
+constexpr u32 V7_STAGE = 512;              // stream bytes staged per group (one 16-byte block per lane; a group reads ~330)
+constexpr u32 V7_WARP_SMEM = 4096 + 32 + 2 * 512;    // V7_WIN + 32 + 2 * V7_STAGE
 constexpr u32 V7_ROUTE_NONE = 0, V7_ROUTE_SEQ = 1, V7_ROUTE_TEAM = 2;
 constexpr u32 V7_BUCKETS = 64;             // chunks are ordered by sequence count / 128 (64 KiB chunks have up to ~8000)
 
@@ -345,7 +345,6 @@ decompress_v7_kernel(const __grid_constant__ V7Params P)
         {
             u8* st = stage0;
             if (lane * 16u < clenA) v7_cp16(st + lane * 16u, srcA + lane * 16u);
-            if (512u + lane * 16u < clenA) v7_cp16(st + 512u + lane * 16u, srcA + 512u + lane * 16u);
             asm volatile("cp.async.commit_group;" ::: "memory");
         }
 
@@ -379,7 +378,6 @@ decompress_v7_kernel(const __grid_constant__ V7Params P)
                 sbuf ^= 1u; sb = nsb;
                 u8* st = stage0 + sbuf * V7_STAGE;
                 if (nsb + lane * 16u < clenA) v7_cp16(st + lane * 16u, srcA + nsb + lane * 16u);
-                if (nsb + 512u + lane * 16u < clenA) v7_cp16(st + 512u + lane * 16u, srcA + nsb + 512u + lane * 16u);
                 asm volatile("cp.async.commit_group;" ::: "memory");
             }
             // the offset rule (lz4/lz4.c:1764 checkOffset; offset 0 rejected as in the oracle): a bad one makes the chunk bad
