@@ -163,7 +163,8 @@ parse_v7_kernel(const __grid_constant__ V7Params P)
                 if (cons >= req + 16) {                                   // the chain jumped past everything requested: restart there,
                     if (landed == req) req = rlo = cons & ~15u;           // once nothing is in flight (a slot must not have two copies pending)
                 } else {                                                  // (req + 16 <= (cons & ~15) + V7_RING follows from req < cons + V7_LOOK)
-                    for (u32 j = 0; j < 6 && req < clen && req < cons + V7_LOOK; j++) V7_REQUEST();
+                    const u32 lim = clen < cons + V7_LOOK ? clen : cons + V7_LOOK;
+                    for (u32 j = 0; j < 6 && req < lim; j++) V7_REQUEST();
                 }
             }
             asm volatile("cp.async.commit_group;" ::: "memory");
@@ -206,6 +207,9 @@ parse_v7_kernel(const __grid_constant__ V7Params P)
                 if (len == RUN_MASK) {                                   // lz4/lz4.c:1707-1729 read_variable_length
                     if (ip + RUN_MASK >= clen) { err = ST_LITLEN_OOB; mode = V7M_IDLE; break; }
                     u32 s;
+                    // a run of 255s, four at a time while they are in the ring and far from the end (the check below holds for all four)
+                    while (ip + 4 <= landed && ip >= rlo && ip + 4 + RUN_MASK < clen &&
+                           (V7_RING_AT(ip) & V7_RING_AT(ip + 1) & V7_RING_AT(ip + 2) & V7_RING_AT(ip + 3)) == 255) { len += 1020; ip += 4; }
                     do {
                         s = V7_RD(ip); ip++; len += s;
                         if (s == 255 && ip + RUN_MASK >= clen) { err = ST_LITLEN_OOB; break; }
