@@ -94,8 +94,9 @@ order_v7_kernel(const __grid_constant__ V7Params P)
 //    token; everything else goes through the general code, which repeats the checks of the reference decoder in
 //    its order and names the violated rule.
 constexpr u32 V7_RING = 512;               // bytes of stream per lane in shared memory (+ 16: the first block again, so that short reads never wrap)
-constexpr u32 V7_LOOK = 384;               // blocks are requested up to this far ahead of the read position
-constexpr u32 V7_G = 4;                    // steps between a request and the first read that may rely on it
+constexpr u32 V7_LOOK = 448;               // blocks are requested up to this far ahead of the read position
+constexpr u32 V7_G = 1;                    // steps between a request and the first read that may rely on it
+constexpr u32 V7_UNROLL = 16;               // common-case sequences per step
 enum : u32 { V7M_TOKEN = 0, V7M_WAITQ = 1, V7M_IDLE = 2 };
 
 __device__ __forceinline__ void v7_cp16(u8* smem_dst, const u8* gsrc)
@@ -164,7 +165,7 @@ parse_v7_kernel(const __grid_constant__ V7Params P)
                     if (landed == req) req = rlo = cons & ~15u;           // once nothing is in flight (a slot must not have two copies pending)
                 } else {                                                  // (req + 16 <= (cons & ~15) + V7_RING follows from req < cons + V7_LOOK)
                     const u32 lim = clen < cons + V7_LOOK ? clen : cons + V7_LOOK;
-                    for (u32 j = 0; j < 6 && req < lim; j++) V7_REQUEST();
+                    for (u32 j = 0; j < 20 && req < lim; j++) V7_REQUEST();
                 }
             }
             asm volatile("cp.async.commit_group;" ::: "memory");
@@ -172,25 +173,30 @@ parse_v7_kernel(const __grid_constant__ V7Params P)
             landed = pend; pend = req;
             qlim = tiny ? 0u : (clen < landed + 5 ? clen : landed + 5) - 8;
         }
-        // ---- common case, no branch.  The token (and the byte behind it) of the CURRENT position were read one step ago
-        //      (tok, te1, valid iff tv): this step reads the match length byte and, at the position the chain moves to if the
-        //      sequence is a common one, the next token. ----
-        const bool lx = (tok >> 4) == RUN_MASK;
-        const u32 Lf = lx ? RUN_MASK + te1 : tok >> 4;
-        const u32 lsrc_f = ip + (lx ? 2u : 1u);
-        const u32 q = lsrc_f + Lf;                                        // position of the offset
-        const bool mx = (tok & ML_MASK) == ML_MASK;
-        const u32 ipn = q + (mx ? 3u : 2u);
-        const u32 m1 = V7_RING_AT(q + 2);
-        const u8* rn = ring + (ipn & (V7_RING - 1));
-        const u32 tokn = rn[0], e1n = rn[1];                              // (whatever is there if it has not landed: tv says)
-        const u32 ml_f = (mx ? ML_MASK + m1 : tok & ML_MASK) + MINMATCH;
-        const u32 cpy_f = op + Lf, nop_f = cpy_f + ml_f;
-        const bool fast = tv && q <= qlim && cpy_f <= lim_cpy && nop_f <= lim_nop && !(lx && te1 == 255) && !(mx && m1 == 255);
-        if (fast) {                                                       // (tv is only ever set in V7M_TOKEN)
-            tab[k++] = v7_pack(op, lsrc_f - mis, ml_f, Lf);
-            op = nop_f;
-            ip = ipn; tok = tokn; te1 = e1n; tv = ipn + 2 <= landed;
+        // ---- common case, no branch, V7_UNROLL sequences per step (what a step costs beside them -- the vote, the ring, the test
+        //      for the general code -- is paid once).  The token (and the byte behind it) of the CURRENT position were read with the
+        //      previous sequence (tok, te1, valid iff tv): a sequence reads its match length byte and, at the position the chain
+        //      moves to if it is a common one, the next token. ----
+        bool fast = false;
+        #pragma unroll
+        for (u32 u = 0; u < V7_UNROLL; u++) {
+            const bool lx = (tok >> 4) == RUN_MASK;
+            const u32 Lf = lx ? RUN_MASK + te1 : tok >> 4;
+            const u32 lsrc_f = ip + (lx ? 2u : 1u);
+            const u32 q = lsrc_f + Lf;                                    // position of the offset
+            const bool mx = (tok & ML_MASK) == ML_MASK;
+            const u32 ipn = q + (mx ? 3u : 2u);
+            const u32 m1 = V7_RING_AT(q + 2);
+            const u8* rn = ring + (ipn & (V7_RING - 1));
+            const u32 tokn = rn[0], e1n = rn[1];                          // (whatever is there if it has not landed: tv says)
+            const u32 ml_f = (mx ? ML_MASK + m1 : tok & ML_MASK) + MINMATCH;
+            const u32 cpy_f = op + Lf, nop_f = cpy_f + ml_f;
+            fast = tv && q <= qlim && cpy_f <= lim_cpy && nop_f <= lim_nop && !(lx && te1 == 255) && !(mx && m1 == 255);
+            if (fast) {                                                   // (tv is only ever set in V7M_TOKEN)
+                tab[k++] = v7_pack(op, lsrc_f - mis, ml_f, Lf);
+                op = nop_f;
+                ip = ipn; tok = tokn; te1 = e1n; tv = ipn + 2 <= landed;
+            }
         }
         // ---- everything else: one sequence through the general code, when its bytes are there (else the lane sits this step out) ----
         // TOKEN: 32 bytes from the token on must have landed (token, length bytes; longer runs of length bytes read global memory)
