@@ -378,7 +378,7 @@ decompress_v5_kernel(const __grid_constant__ V5Params P)
 template <u32 T>
 inline cudaError_t v5_launch_t(const u8* in, const u64* in_off, const u64* csz, const u64* out_off, const u64* usz,
                                u8* out, u32* status, u32* bad, u32 n, u32* ticket, int sm_count, cudaStream_t st, u32 cap_all,
-                               const u32* list, const u32* list_count)
+                               const u32* list, const u32* list_count, bool ticket_cleared = false)
 {
     const u32 teams_per_block = V2_BLOCK / T;
     int per_sm = 0;
@@ -388,8 +388,10 @@ inline cudaError_t v5_launch_t(const u8* in, const u64* in_off, const u64* csz, 
     unsigned grid = (unsigned)(sm_count * per_sm);
     const unsigned need = (n + teams_per_block - 1) / teams_per_block;
     if (grid > need) grid = need;
-    e = cudaMemsetAsync(ticket, 0, sizeof(u32), st);
-    if (e != cudaSuccess) return e;
+    if (!ticket_cleared) {
+        e = cudaMemsetAsync(ticket, 0, sizeof(u32), st);
+        if (e != cudaSuccess) return e;
+    }
     const V5Params P{ in, in_off, csz, out_off, usz, out, status, bad, ticket, n, cap_all, list, list_count };
     decompress_v5_kernel<T><<<grid, V2_BLOCK, 0, st>>>(P);
     return cudaGetLastError();
@@ -398,11 +400,11 @@ inline cudaError_t v5_launch_t(const u8* in, const u64* in_off, const u64* csz, 
 inline cudaError_t v5_launch_decompress(int team, const u8* in, const u64* in_off, const u64* csz, const u64* out_off,
                                         const u64* usz, u8* out, u32* status, u32* bad, u32 n, u32* ticket,
                                         int sm_count, cudaStream_t st, u32 cap_all = 0,
-                                        const u32* list = nullptr, const u32* list_count = nullptr)
+                                        const u32* list = nullptr, const u32* list_count = nullptr, bool ticket_cleared = false)
 {
-    if (team == 16) return v5_launch_t<16>(in, in_off, csz, out_off, usz, out, status, bad, n, ticket, sm_count, st, cap_all, list, list_count);
-    if (team == 4) return v5_launch_t<4>(in, in_off, csz, out_off, usz, out, status, bad, n, ticket, sm_count, st, cap_all, list, list_count);
-    return v5_launch_t<8>(in, in_off, csz, out_off, usz, out, status, bad, n, ticket, sm_count, st, cap_all, list, list_count);
+    if (team == 16) return v5_launch_t<16>(in, in_off, csz, out_off, usz, out, status, bad, n, ticket, sm_count, st, cap_all, list, list_count, ticket_cleared);
+    if (team == 4) return v5_launch_t<4>(in, in_off, csz, out_off, usz, out, status, bad, n, ticket, sm_count, st, cap_all, list, list_count, ticket_cleared);
+    return v5_launch_t<8>(in, in_off, csz, out_off, usz, out, status, bad, n, ticket, sm_count, st, cap_all, list, list_count, ticket_cleared);
 }
 
 }  // namespace lz4b200

@@ -38,6 +38,7 @@ constexpr int V7_WARPS = 8;                // warps per CTA of the lane-per-sequ
 constexpr u32 V7_STAGE = 512;              // stream bytes staged per group (one 16-byte block per lane; a group reads ~330)
 constexpr u32 V7_WARP_SMEM = 4096 + 32 + 2 * 512;    // V7_WIN + 32 + 2 * V7_STAGE
 constexpr u32 V7_ROUTE_NONE = 0, V7_ROUTE_SEQ = 1, V7_ROUTE_TEAM = 2;
+constexpr u32 V7_ZERO_WORDS = 2 * 64 + 4;  // one block per slice, cleared by ONE memset per pass: bucket counters, team_count, the two work tickets
 constexpr u32 V7_BUCKETS = 64;             // chunks are ordered by sequence count / 128 (64 KiB chunks have up to ~8000)
 
 // entries of the table a chunk may need: sequences (>= 4 output bytes each but the last), literal pieces, terminator
@@ -122,7 +123,9 @@ parse_v7_kernel(const __grid_constant__ V7Params P)
         const u64 base = v7_entries_for(P.out_off[c] - P.out_off[0], c);
         if (clen64 == n64) {
             route = n64 >= 4096 ? V7_ROUTE_TEAM : V7_ROUTE_SEQ;        // raw chunk (_lzbench/lzbench.cpp:311-315): a plain copy
-        } else if (n64 > V7_MAX_CHUNK || clen64 > 0xFFFFu || base + v7_entries_for(n64, 1) > P.table_cap) {
+        } else if (n64 > V7_MAX_CHUNK || clen64 > 0xFFFFu || base + v7_entries_for(n64, 1) > P.table_cap ||
+                   clen64 * 85 < n64 ||                                   // fewer than n / 256 sequences (>= 3 stream bytes each): the team decoder's case, no need to walk
+                   clen64 + (n64 >> 5) >= n64) {                           // hardly compressed: long literal runs, the team decoder's case as well
             route = V7_ROUTE_TEAM;
         } else if (n64 == 0 || clen64 == 0) {                            // lz4/lz4.c:1776-1782
             err = (n64 == 0 && clen64 == 1 && src[0] == 0) ? ST_OK : ST_EMPTY;
@@ -553,9 +556,8 @@ decompress_v7_kernel(const __grid_constant__ V7Params P)
 
 inline cudaError_t v7_launch_parse(const V7Params& P, cudaStream_t st)
 {
-    cudaError_t e = cudaMemsetAsync(P.team_count, 0, sizeof(u32), st);
-    if (e != cudaSuccess) return e;
-    e = cudaMemsetAsync(P.bucket, 0, 2 * V7_BUCKETS * sizeof(u32), st);
+    // P.bucket points at the slice's zero block: [0, 2 V7_BUCKETS) counters, then team_count, ticket of pass 2, ticket of the team decoder
+    cudaError_t e = cudaMemsetAsync(P.bucket, 0, V7_ZERO_WORDS * sizeof(u32), st);
     if (e != cudaSuccess) return e;
     parse_v7_kernel<<<(P.n_chunks + 31) / 32, 32, 0, st>>>(P);
     order_v7_kernel<<<(P.n_chunks + 255) / 256, 256, 0, st>>>(P);
@@ -574,9 +576,7 @@ inline cudaError_t v7_launch_decompress(const V7Params& P, int sm_count, cudaStr
     unsigned grid = (unsigned)(sm_count * per_sm);
     const unsigned need = (P.n_chunks + V7_WARPS - 1) / V7_WARPS;
     if (grid > need) grid = need;
-    e = cudaMemsetAsync(P.ticket, 0, sizeof(u32), st);
-    if (e != cudaSuccess) return e;
-    decompress_v7_kernel<<<grid, V7_WARPS * 32, smem, st>>>(P);
+    decompress_v7_kernel<<<grid, V7_WARPS * 32, smem, st>>>(P);               // (P.ticket was cleared with the zero block)
     return cudaGetLastError();
 }
 

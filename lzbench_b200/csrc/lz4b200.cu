@@ -128,7 +128,7 @@ struct lz4b200_ctx {
     size_t v7_chunks = 0;               // chunk count the u32 arrays are laid out for (current call)
     size_t v7_table_chunks = 0;         // chunks the table has room for (current call): all of a host call's, one sub-batch of a device call's
     size_t v7_per_chunk = 0;            // table entries reserved per chunk (current call)
-    size_t v7_min_chunk = 32769;        // v7 only pays on chunks above 32 KiB (1 GiB mixed: 4 KiB 143 vs 356 GB/s, 32 KiB 238 vs 260, 64 KiB 262 vs 236); "kernels=v7" forces it
+    size_t v7_min_chunk = 16385;        // v7 pays on chunks above 16 KiB (1 GiB mixed, v7 vs v5: 8 KiB 275 vs 317 GB/s, 16 KiB 302 vs 299, 32 KiB 327 vs 261, 64 KiB 316 vs 230); "kernels=v7" forces it
     // buffers behind the host entry points
     DevBuf d_plain, d_packed;
     PinBuf h_sizes;                     // u64[2*n_chunks + MAX_SLICES + 2]
@@ -147,7 +147,7 @@ constexpr size_t SC_FCK = 28;           // u32  frame container: block checksum 
 constexpr size_t SC_TICKETS = 256;      // u32[MAX_SLICES] work tickets, one per slice
 constexpr size_t SC_TICKETS2 = 512;     // u32[MAX_SLICES] second ticket per slice (two decoders side by side)
 constexpr size_t SC_NJOBS = 1024;        // u64[MAX_SLICES] job counts of the segmented compressor, one per slice
-constexpr size_t SC_TEAMCOUNT = 2048;    // u32[MAX_SLICES] v7: chunks left to the team decoder, one counter per slice
+constexpr size_t SC_TEAMCOUNT = 2048;    // (unused since the v7 zero block)
 constexpr size_t SC_RUNNING = 4096;     // u64[MAX_SLICES] running compressed totals after each slice
 constexpr size_t SC_BYTES = 8192;
 
@@ -216,7 +216,7 @@ void ensure_v7(lz4b200_ctx* c, size_t n, size_t table_chunks, size_t max_chunk)
     c->v7_chunks = c->v7_table_chunks = 0;
     if (c->kernel_gen != 7 || max_chunk > V7_MAX_CHUNK || max_chunk < c->v7_min_chunk || n == 0) return;
     c->v7_per_chunk = (size_t)v7_entries_for(max_chunk, 1) + 2;      // + 2: the floors of a ragged prefix sum
-    if (c->v7_u32.ensure((4 * n + 2 * V7_BUCKETS * lz4b200_ctx::MAX_SLICES) * sizeof(u32)) != cudaSuccess ||
+    if (c->v7_u32.ensure((4 * n + V7_ZERO_WORDS * lz4b200_ctx::MAX_SLICES) * sizeof(u32)) != cudaSuccess ||
         c->v7_table.ensure(table_chunks * c->v7_per_chunk * sizeof(u64)) != cudaSuccess) { cudaGetLastError(); return; }
     c->v7_chunks = n; c->v7_table_chunks = table_chunks;
 }
@@ -241,8 +241,8 @@ Scratch scratch_at(lz4b200_ctx* c, size_t first_chunk, size_t stride, int slice)
         }
         u32* b = (u32*)c->v7_u32.p;
         s.v7_nseq = b + first_chunk; s.v7_route = b + c->v7_chunks + first_chunk; s.v7_list = b + 2 * c->v7_chunks + first_chunk;
-        s.v7_order = b + 3 * c->v7_chunks + first_chunk; s.v7_bucket = b + 4 * c->v7_chunks + 2 * V7_BUCKETS * slice;
-        s.v7_count = (u32*)((u8*)c->scalars.p + SC_TEAMCOUNT) + slice;
+        s.v7_order = b + 3 * c->v7_chunks + first_chunk; s.v7_bucket = b + 4 * c->v7_chunks + V7_ZERO_WORDS * slice;   // the slice's zero block
+        s.v7_count = s.v7_bucket + 2 * V7_BUCKETS;
     }
     s.first_chunk = first_chunk;
     return s;
@@ -384,7 +384,7 @@ int decompress_slice(lz4b200_ctx* c, const u8* d_in, const u64* d_csz, const u64
             }
             const size_t b2 = b + mA, m2 = m - mA;
             if (m2) {
-                V7Params P{ d_in, s.coff + b2, d_csz + b2, s.uoff + b2, d_usz + b2, d_out, s.status + b2, d_bad, s.ticket, (u32)m2, cap_all,
+                V7Params P{ d_in, s.coff + b2, d_csz + b2, s.uoff + b2, d_usz + b2, d_out, s.status + b2, d_bad, s.v7_count + 1, (u32)m2, cap_all,
                             s.v7_table, s.v7_cap, s.v7_nseq + b2, s.v7_route + b2, s.v7_list + b2, s.v7_count, s.v7_order + b2, s.v7_bucket };
                 CU(v7_launch_parse(P, st));
                 if (mA) {
@@ -395,7 +395,7 @@ int decompress_slice(lz4b200_ctx* c, const u8* d_in, const u64* d_csz, const u64
                 }
                 CU(v7_launch_decompress(P, c->sm_count, st));
                 CU(v5_launch_decompress(team == 32 ? 16 : team, d_in, s.coff + b2, d_csz + b2, s.uoff + b2, d_usz + b2, d_out,
-                                        s.status + b2, d_bad, (u32)m2, s.ticket, c->sm_count, st, cap_all, s.v7_list + b2, s.v7_count));
+                                        s.status + b2, d_bad, (u32)m2, s.v7_count + 2, c->sm_count, st, cap_all, s.v7_list + b2, s.v7_count, true));
                 c->launches += 4;
             }
             if (mA) CU(cudaStreamWaitEvent(st, c->ev_join[s.slice], 0));
@@ -653,7 +653,7 @@ int lz4b200_set_option(lz4b200_ctx* c, const char* key, const char* value)
         if (!strcmp(value, "v5")) { c->kernel_gen = 5; c->compress_gen = 2; return 0; }
         if (!strcmp(value, "v6")) { c->kernel_gen = 6; c->compress_gen = 2; return 0; }
         if (!strcmp(value, "v7") || !strcmp(value, "default")) {
-            c->kernel_gen = 7; c->compress_gen = 2; c->v7_min_chunk = strcmp(value, "v7") ? 32769 : 0;
+            c->kernel_gen = 7; c->compress_gen = 2; c->v7_min_chunk = strcmp(value, "v7") ? 16385 : 0;
             return 0;
         }
     }
