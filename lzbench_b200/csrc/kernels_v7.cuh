@@ -34,7 +34,7 @@ constexpr u32 V7_WIN = 4096;               // bytes of the per-warp output windo
 constexpr u32 V7_KEEP = 1008;              // history kept below a group when the window slides
 constexpr u32 V7_LPIECE = 8191;            // literal runs are cut into entries of at most this many bytes (13-bit field)
 constexpr u32 V7_MAX_CHUNK = 65536;
-constexpr int V7_WARPS = 8;                // warps per CTA of the lane-per-sequence kernel
+constexpr int V7_WARPS = 4;                // warps per CTA of the lane-per-sequence kernel
 constexpr u32 V7_STAGE = 512;              // stream bytes staged per group (one 16-byte block per lane; a group reads ~330)
 constexpr u32 V7_WARP_SMEM = 4096 + 32 + 2 * 512;    // V7_WIN + 32 + 2 * V7_STAGE
 constexpr u32 V7_ROUTE_NONE = 0, V7_ROUTE_SEQ = 1, V7_ROUTE_TEAM = 2;
@@ -319,7 +319,7 @@ __device__ __forceinline__ void v7_flush(u8* dstv, const u8* win, u32 win_base, 
     }
 }
 
-__global__ void __launch_bounds__(V7_WARPS * 32, 3)
+__global__ void __launch_bounds__(V7_WARPS * 32, 7)
 decompress_v7_kernel(const __grid_constant__ V7Params P)
 {
     // per warp: the output window, then two buffers for the stream bytes of the next group (on their way while this one runs)
