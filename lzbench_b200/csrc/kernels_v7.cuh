@@ -106,12 +106,13 @@ __device__ __forceinline__ void v7_cp16(u8* smem_dst, const u8* gsrc)
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(d), "l"(gsrc) : "memory");
 }
 
+template <u32 LANES>                      // chunks per warp: 32 leaves one warp per scheduler on a 16 384-chunk batch; fewer lanes = more warps to interleave
 __global__ void __launch_bounds__(32)
 parse_v7_kernel(const __grid_constant__ V7Params P)
 {
-    __shared__ __align__(16) u8 ring_all[32][V7_RING + 16];
-    const u32 c = blockIdx.x * 32 + threadIdx.x;
-    const bool have = c < P.n_chunks;
+    __shared__ __align__(16) u8 ring_all[LANES][V7_RING + 16];
+    const u32 c = blockIdx.x * LANES + threadIdx.x;
+    const bool have = threadIdx.x < LANES && c < P.n_chunks;
     u32 err = ST_OK, route = V7_ROUTE_NONE, k = 0;
     u32 mode = V7M_IDLE;
     const u8* srcA = nullptr;              // the stream, from its start rounded down to 16 bytes: positions below count from here
@@ -137,7 +138,7 @@ parse_v7_kernel(const __grid_constant__ V7Params P)
             route = V7_ROUTE_SEQ; mode = V7M_TOKEN;
         }
     }
-    u8* const ring = ring_all[threadIdx.x];
+    u8* const ring = ring_all[threadIdx.x & (LANES - 1)];
     u32 req = 0;                           // blocks below this position have been requested (multiple of 16)
     u32 landed = 0, pend = 0;              // positions below `landed` have arrived
     u32 rlo = 0;                           // ... and are in the ring if not below its last restart (and not yet overwritten: see V7_RD)
@@ -554,12 +555,14 @@ decompress_v7_kernel(const __grid_constant__ V7Params P)
     }
 }
 
-inline cudaError_t v7_launch_parse(const V7Params& P, cudaStream_t st)
+inline cudaError_t v7_launch_parse(const V7Params& P, cudaStream_t st, int lanes = 32)
 {
     // P.bucket points at the slice's zero block: [0, 2 V7_BUCKETS) counters, then team_count, ticket of pass 2, ticket of the team decoder
     cudaError_t e = cudaMemsetAsync(P.bucket, 0, V7_ZERO_WORDS * sizeof(u32), st);
     if (e != cudaSuccess) return e;
-    parse_v7_kernel<<<(P.n_chunks + 31) / 32, 32, 0, st>>>(P);
+    if (lanes == 8) parse_v7_kernel<8><<<(P.n_chunks + 7) / 8, 32, 0, st>>>(P);
+    else if (lanes == 16) parse_v7_kernel<16><<<(P.n_chunks + 15) / 16, 32, 0, st>>>(P);
+    else parse_v7_kernel<32><<<(P.n_chunks + 31) / 32, 32, 0, st>>>(P);
     order_v7_kernel<<<(P.n_chunks + 255) / 256, 256, 0, st>>>(P);
     return cudaGetLastError();
 }

@@ -17,6 +17,7 @@
 #include "kernels_v7.cuh"
 #include "kernels_c1.cuh"
 #include "kernels_c2.cuh"
+#include "kernels_c3.cuh"
 #include "segmented.cuh"
 #include "frame.cuh"
 #include "staging.cuh"
@@ -106,6 +107,8 @@ struct lz4b200_ctx {
     cudaStream_t d2h_stream = nullptr;
     cudaStream_t aux_stream = nullptr;  // v7 decode: the team decoder's share of a large batch runs beside the sequence-table pass
     cudaEvent_t ev_fork[MAX_SLICES] = {}, ev_join[MAX_SLICES] = {};
+    int c3_workers = 8;                 // compress c3: worker warps per CTA beside the table warp (option "c3workers")
+    int v7_lanes = 32;                  // v7 pass 1: chunks per warp (option "planes")
     int split = -1;                     // percent of a large batch given to the team decoder (-1 = automatic, option "split")
     cudaStream_t h2d_stream = nullptr;  // ALL inbound bulk copies: spread over the compute streams they lose a third of the link (measured: 1 GiB each way in 32 ms on 8 streams, 22.6 ms on one)
     cudaEvent_t ev_sizes = nullptr, ev_scan[MAX_SLICES] = {}, ev_done[MAX_SLICES] = {}, ev_in[MAX_SLICES] = {};
@@ -292,7 +295,11 @@ int compress_slice(lz4b200_ctx* c, const u8* d_in, const u64* d_usz, size_t n, s
                               (u32)c->accel, c->c1mode));
         seg_stitch_size_kernel<<<gb, 256, 0, st>>>(sa, s.stage, slot_stride_for(SEG_BYTES), d_csz, (u32)n);
         c->launches += 5;
-    } else if (c->compress_gen == 2 && c1_compress_supported(max_chunk)) {
+    } else if (c->compress_gen == 3 && c->accel == 1 && c1_compress_supported(max_chunk)) {
+        CU(c3_launch_compress(d_in, s.uoff, d_usz, s.stage, stride, d_csz, (u32)n, s.ticket, c->sm_count, st,
+                              c->prof_on ? (u64*)c->prof.p : nullptr, c->c3_workers));
+        c->launches++;
+    } else if (c->compress_gen >= 2 && c1_compress_supported(max_chunk)) {
         CU(c2_launch_compress(d_in, s.uoff, d_usz, s.stage, stride, d_csz, (u32)n, s.ticket, c->sm_count, st, nullptr, nullptr, nullptr,
                               nullptr, c->prof_on ? (u64*)c->prof.p : nullptr, (u32)c->accel, c->c1mode));
         c->launches++;
@@ -386,7 +393,7 @@ int decompress_slice(lz4b200_ctx* c, const u8* d_in, const u64* d_csz, const u64
             if (m2) {
                 V7Params P{ d_in, s.coff + b2, d_csz + b2, s.uoff + b2, d_usz + b2, d_out, s.status + b2, d_bad, s.v7_count + 1, (u32)m2, cap_all,
                             s.v7_table, s.v7_cap, s.v7_nseq + b2, s.v7_route + b2, s.v7_list + b2, s.v7_count, s.v7_order + b2, s.v7_bucket };
-                CU(v7_launch_parse(P, st));
+                CU(v7_launch_parse(P, st, c->v7_lanes));
                 if (mA) {
                     CU(v5_launch_decompress(16, d_in, s.coff + b, d_csz + b, s.uoff + b, d_usz + b, d_out, s.status + b, d_bad, (u32)mA,
                                             s.ticket2, c->sm_count, c->aux_stream, cap_all));
@@ -661,6 +668,7 @@ int lz4b200_set_option(lz4b200_ctx* c, const char* key, const char* value)
         if (!strcmp(value, "v0")) { c->compress_gen = 0; return 0; }
         if (!strcmp(value, "v1")) { c->compress_gen = 1; return 0; }
         if (!strcmp(value, "v2")) { c->compress_gen = 2; return 0; }
+        if (!strcmp(value, "v3")) { c->compress_gen = 3; return 0; }
     }
     if (!strcmp(key, "c1mode")) { c->c1mode = atoi(value); return 0; }
     if (!strcmp(key, "accel")) {                        // LZ4_compress_fast's acceleration (lz4/lz4.c:1352-1375); the lz4fast levels of lzbench
@@ -680,6 +688,8 @@ int lz4b200_set_option(lz4b200_ctx* c, const char* key, const char* value)
         int p = atoi(value);
         if (p >= -1 && p <= 90) { c->split = p; return 0; }
     }
+    if (!strcmp(key, "c3workers")) { const int v = atoi(value); if (v == 8 || v == 12 || v == 16) { c->c3_workers = v; return 0; } return -1; }
+    if (!strcmp(key, "planes")) { const int v = atoi(value); if (v == 8 || v == 16 || v == 32) { c->v7_lanes = v; return 0; } return -1; }
     if (!strcmp(key, "ramp")) { c->ramp = value[0] == '1'; return 0; }
     if (!strcmp(key, "h2d")) { c->own_h2d = strcmp(value, "shared") != 0; return 0; }
     if (!strcmp(key, "host_register")) { c->host_register = value[0] == '1'; return 0; }

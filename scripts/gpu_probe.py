@@ -44,11 +44,15 @@ for kind in kinds:
     d_bad = torch.zeros(1, dtype=torch.int32, device="cuda")
     s = torch.cuda.current_stream().cuda_stream
     for gen in gens:
-        ctx.set_option("accel", "1"); ctx.set_option("split", "-1")
+        ctx.set_option("accel", "1"); ctx.set_option("split", "-1"); ctx.set_option("planes", "32")
         if gen.startswith("v7s"):                        # v7s<percent of a large batch on the team decoder>
             ctx.set_option("kernels", "v7"); ctx.set_option("split", gen[3:])
+        elif gen.startswith("v7p"):                      # v7p<chunks per warp in the table pass>
+            ctx.set_option("kernels", "v7"); ctx.set_option("planes", gen[3:])
         elif gen.startswith("c2a"):                       # c2a<acceleration>
             ctx.set_option("kernels", "v5"); ctx.set_option("compress", "v2"); ctx.set_option("accel", gen[3:])
+        elif gen.startswith("c3"):                       # c3[w<worker warps>]
+            ctx.set_option("kernels", "default"); ctx.set_option("compress", "v3"); ctx.set_option("c3workers", gen[3:] or "8")
         elif gen in ("c1", "c2"):
             ctx.set_option("kernels", "v4"); ctx.set_option("compress", "v" + gen[1])
         elif gen.startswith("c1m"):
@@ -79,7 +83,12 @@ for kind in kinds:
             tot = sum(pr[:8]) or 1
             print("   decode phases [ticket,load,parse,scan,literals,matches,(coop),store] %:",
                   [round(100 * x / tot, 1) for x in pr[:7]], "cycles/chunk", tot // n_chunks, flush=True)
-        if gen in ("c2", "v5t8") and os.environ.get("PROF"):
+        if gen.startswith("c3") and os.environ.get("PROF"):
+            ctx.set_option("prof", "1"); comp(); pr = ctx.debug_prof(); ctx.set_option("prof", "0")
+            tiles = pr[4] or 1
+            print("   c3 cycles/tile (worker thread 0): long literals + V + R %d | P beside H %d | E pass A %d | E pass B %d | stage/chunk %d | tiles/chunk %.1f"
+                  % (pr[0] // tiles, pr[1] // tiles, pr[2] // tiles, pr[3] // tiles, pr[5] // n_chunks, tiles / n_chunks), flush=True)
+        elif gen in ("c2", "v5t8") and os.environ.get("PROF"):
             ctx.set_option("prof", "1"); comp(); pr = ctx.debug_prof(); ctx.set_option("prof", "0")
             tiles = n_chunks * 16
             print("   c2 cycles/tile: A match %d, A wait-empty %d | B wait-full %d, B parse %d, B emit %d | stage/chunk %d | rounds/tile %.2f"
