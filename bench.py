@@ -183,14 +183,25 @@ def _ref_trampolines():
     return C.cast(lib.ref_plugin_lz4_compress, C.c_void_p), C.cast(lib.ref_plugin_lz4_decompress, C.c_void_p)
 
 
+def workload_config(args, world):
+    """The `config` object of the JSON line: what defines the workload and nothing else, so that both arms print the same one."""
+    n = args.size_mib << 20
+    return {"workload": f"LZ4 block decompress, {args.chunk} B chunks, {args.size_mib} MiB '{args.corpus}' corpus per GPU "
+                        f"(BASELINE configs[1]; configs[3] sharding when n_gpus>1)",
+            "chunk_bytes": args.chunk, "chunks_per_gpu": (n + args.chunk - 1) // args.chunk, "corpus": args.corpus,
+            "seed": 2 if world == 1 else 3,
+            "l2": "inputs larger than L2: a step writes %.0f MB per GPU and reads its compressed image vs 126 MB L2" % (n / 1e6)}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import lzbench_b200 as L
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     threads = os.cpu_count() or 1
-    n = args.cpu_sample_mib << 20
-    plain = L.corpus(args.corpus, n, seed=2)
+    n = min(args.cpu_sample_mib, args.size_mib) << 20
+    plain = L.corpus(args.corpus, n, seed=2 if world == 1 else 3)
     for _ in range(args.warmup):
         cpu_baseline(plain, args.chunk, min(n, 32 << 20), threads)
     t0 = time.perf_counter()
@@ -206,10 +217,10 @@ def run_reference(args):
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * (n / GB) / dec, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u8", "data": "synthetic",
-        "config": {"workload": f"LZ4 block decompress, {args.chunk} B chunks, {args.corpus} corpus, CPU lz4 1.9.3 under "
-                               f"lzbench's chunk loop", "chunk_bytes": args.chunk, "corpus": args.corpus, "seed": 2},
+        "config": workload_config(args, world),
+        "details": {"what": "CPU lz4 1.9.3 (the reference's own lz4.c behind its plugin wrappers) under lzbench's chunk loop, all host threads"},
         "cpu_baseline": {"value": dec, "unit": "GB/s", "cores": threads, "kind": r["kind"],
-                         "sample": f"first {args.cpu_sample_mib} MiB of the workload per step, {threads} threads, "
+                         "sample": f"first {n >> 20} MiB of the workload per step, {threads} threads, "
                                    f"contiguous chunk ranges per thread", "compress_GBps": com,
                          "ratio_pct": 100.0 * r["compressed_bytes"] / r["sample_bytes"]},
         "e2e": {"value": dec, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -375,13 +386,10 @@ def run_b200(args):
         "value": world * U / (d_ms * 1e-3) / GB, "unit": "GB/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": d_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u8", "data": "synthetic",
-        "config": {"workload": f"LZ4 block decompress, {chunk} B chunks, {args.size_mib} MiB '{args.corpus}' corpus per GPU "
-                               f"(BASELINE configs[1]; configs[3] sharding when n_gpus>1)",
-                   "chunk_bytes": chunk, "chunks_per_gpu": n_chunks, "corpus": args.corpus, "seed": seed,
-                   "compressed_by": "lz4_b200 (standard LZ4 blocks, cross-decode tested)",
-                   "compressed_pct": 100.0 * Cb / U, "kernels": args.kernels or "default",
-                   "l2": "inputs larger than L2: each step reads %.0f MB and writes %.0f MB vs 126 MB L2" % (Cb / 1e6, U / 1e6),
-                   "shard_base_offset": shard_base},
+        "config": workload_config(args, world),
+        "details": {"compressed_by": "lz4_b200 (standard LZ4 blocks, cross-decode tested)", "compressed_pct": 100.0 * Cb / U,
+                    "kernels": args.kernels or "default", "shard_base_offset": shard_base,
+                    "bytes_per_step": "reads %.0f MB, writes %.0f MB" % (Cb / 1e6, U / 1e6)},
         "roofline": roof(d_kt, "decompress"),
         "e2e": {"value": world * U / e2e_d / GB, "unit": "GB/s", "h2d_bytes_per_step": int(Cb + 16 * n_chunks),
                 "d2h_bytes_per_step": int(U + 4), "ms_per_step": e2e_d * 1e3,

@@ -297,7 +297,7 @@ int compress_slice(lz4b200_ctx* c, const u8* d_in, const u64* d_usz, size_t n, s
         c->launches += 5;
     } else if (c->compress_gen == 3 && c->accel == 1 && c1_compress_supported(max_chunk)) {
         CU(c3_launch_compress(d_in, s.uoff, d_usz, s.stage, stride, d_csz, (u32)n, s.ticket, c->sm_count, st,
-                              c->prof_on ? (u64*)c->prof.p : nullptr, c->c3_workers));
+                              c->prof_on ? (u64*)c->prof.p : nullptr));
         c->launches++;
     } else if (c->compress_gen >= 2 && c1_compress_supported(max_chunk)) {
         CU(c2_launch_compress(d_in, s.uoff, d_usz, s.stage, stride, d_csz, (u32)n, s.ticket, c->sm_count, st, nullptr, nullptr, nullptr,

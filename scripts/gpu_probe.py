@@ -52,7 +52,7 @@ for kind in kinds:
         elif gen.startswith("c2a"):                       # c2a<acceleration>
             ctx.set_option("kernels", "v5"); ctx.set_option("compress", "v2"); ctx.set_option("accel", gen[3:])
         elif gen.startswith("c3"):                       # c3[w<worker warps>]
-            ctx.set_option("kernels", "default"); ctx.set_option("compress", "v3"); ctx.set_option("c3workers", gen[3:] or "8")
+            ctx.set_option("kernels", "default"); ctx.set_option("compress", "v3")
         elif gen in ("c1", "c2"):
             ctx.set_option("kernels", "v4"); ctx.set_option("compress", "v" + gen[1])
         elif gen.startswith("c1m"):
@@ -86,8 +86,9 @@ for kind in kinds:
         if gen.startswith("c3") and os.environ.get("PROF"):
             ctx.set_option("prof", "1"); comp(); pr = ctx.debug_prof(); ctx.set_option("prof", "0")
             tiles = pr[4] or 1
-            print("   c3 cycles/tile (worker thread 0): long literals + V + R %d | P beside H %d | E pass A %d | E pass B %d | stage/chunk %d | tiles/chunk %.1f"
-                  % (pr[0] // tiles, pr[1] // tiles, pr[2] // tiles, pr[3] // tiles, pr[5] // n_chunks, tiles / n_chunks), flush=True)
+            print("   c3 cycles/tile: H+V %d | T %d | P %d | E %d | step %d | stage/chunk %d | tiles/chunk %.1f"
+                  % (pr[0] // tiles, pr[1] // tiles, pr[2] // tiles, pr[3] // tiles, pr[6] // tiles, pr[5] // n_chunks, tiles / n_chunks), flush=True)
+            print("   c3 parse: second warp %d cycles/tile; rounds/tile %.2f, steps/tile %.1f (both warps)" % (pr[9] // tiles, pr[7] / tiles, pr[8] / tiles), flush=True)
         elif gen in ("c2", "v5t8") and os.environ.get("PROF"):
             ctx.set_option("prof", "1"); comp(); pr = ctx.debug_prof(); ctx.set_option("prof", "0")
             tiles = n_chunks * 16

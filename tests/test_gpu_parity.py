@@ -65,6 +65,67 @@ def test_compress_cross_decodes_and_ratio(gpu_ctx, kernels, chunk, kind, seed):
     assert total <= RATIO_TOLERANCE * int(ref_compr.sum()) + 64, (total, int(ref_compr.sum()))
 
 
+@pytest.mark.parametrize("chunk", [4096, 16384, 65536, 100000])
+@pytest.mark.parametrize("kind,seed", CORPORA)
+def test_compress_c3_cross_decodes_and_ratio(gpu_ctx, chunk, kind, seed):
+    """The generation-3 compressor (kernels_c3.cuh, option compress=v3; chunks above 64 KiB stay on c2's segments): same bars."""
+    gpu_ctx.set_option("compress", "v3")
+    n = 2 * (1 << 20) + 777
+    data = L.corpus(kind, n, seed=seed)
+    cs = L.chunk_list(n, chunk)
+    packed, compr, total = gpu_ctx.compress_batch(data, cs)
+    assert total > 0 and int(compr.sum()) == total
+    check_gpu_blocks_with_reference(data, packed[:total], compr, cs)
+    _, ref_compr = O.oracle_chunked_compress(data, cs)
+    assert total <= RATIO_TOLERANCE * int(ref_compr.sum()) + 64, (total, int(ref_compr.sum()))
+    out, r = gpu_ctx.decompress_batch(packed[:total], compr, cs)
+    assert r == n and np.array_equal(out, data)
+
+
+def test_compress_c3_small_ragged_and_misaligned_chunks(gpu_ctx):
+    """c3 on chunk lists whose chunks start at any byte alignment (the realigning load) and have any size from 1 byte up."""
+    gpu_ctx.set_option("compress", "v3")
+    rng = np.random.default_rng(7)
+    sizes = [1, 2, 5, 11, 12, 13, 14, 15, 16, 17, 31, 32, 33, 63, 64, 65, 100, 255, 256, 270, 271, 1000, 2047, 2048, 2049,
+             2059, 2060, 2061, 4095, 4097, 6143, 6156, 65535, 65536, 65533, 40000]
+    sizes += [int(x) for x in rng.integers(1, 9000, 300)]
+    cs = np.asarray(sizes, dtype=np.uint64)
+    n = int(cs.sum())
+    for kind, seed in CORPORA:
+        data = L.corpus(kind, n, seed=seed)
+        packed, compr, total = gpu_ctx.compress_batch(data, cs)
+        check_gpu_blocks_with_reference(data, packed[:total], compr, cs)
+        out, r = gpu_ctx.decompress_batch(packed[:total], compr, cs)
+        assert r == n and np.array_equal(out, data)
+        _, ref_compr = O.oracle_chunked_compress(data, cs)
+        assert total <= RATIO_TOLERANCE * int(ref_compr.sum()) + 8 * len(cs), (kind, total, int(ref_compr.sum()))
+
+
+def test_compress_c3_structured_data(gpu_ctx):
+    """Data that stresses the run logic of c3: short periods (every position its own run), long matches that start in one
+    tile and end many tiles later, matches at the maximum offset, a chunk that is one match."""
+    gpu_ctx.set_option("compress", "v3")
+    rng = np.random.default_rng(11)
+    parts = []
+    for period in (1, 2, 3, 5, 7, 12, 31, 33, 63, 64, 65, 127, 255, 256, 257, 1000, 2047, 2048, 2049, 5000):
+        pat = rng.integers(0, 256, period, dtype=np.uint8)
+        parts.append(np.tile(pat, 65536 // period + 1)[:65536])
+    blk = rng.integers(0, 256, 30000, dtype=np.uint8)                    # a long block seen twice, 65 535 bytes apart at most
+    far = np.concatenate([blk, rng.integers(0, 256, 65536 - 2 * 30000, dtype=np.uint8), blk])
+    parts.append(far[:65536])
+    words = [bytes(rng.integers(97, 123, int(k), dtype=np.uint8)) for k in rng.integers(2, 9, 50)]
+    text = b" ".join(words[int(i)] for i in rng.integers(0, 50, 20000))
+    parts.append(np.frombuffer(text[:65536], dtype=np.uint8))
+    data = np.concatenate(parts)
+    cs = L.chunk_list(len(data), 65536)
+    packed, compr, total = gpu_ctx.compress_batch(data, cs)
+    check_gpu_blocks_with_reference(data, packed[:total], compr, cs)
+    _, ref_compr = O.oracle_chunked_compress(data, cs)
+    assert total <= RATIO_TOLERANCE * int(ref_compr.sum()) + 64 * len(cs), (total, int(ref_compr.sum()))
+    out, r = gpu_ctx.decompress_batch(packed[:total], compr, cs)
+    assert r == len(data) and np.array_equal(out, data)
+
+
 @pytest.mark.parametrize("kernels", ["v0", "v1", "v2", "v3", "v4", "v5", "v6", "v7"])
 @pytest.mark.parametrize("chunk", [4096, 65536, 100000, 1 << 20])
 @pytest.mark.parametrize("kind,seed", CORPORA)
