@@ -115,17 +115,21 @@ int lz4b200_debug_prof(lz4b200_ctx* ctx, uint64_t* out16);
  *              ring, long literal runs on the fast path, slow path out of line; "v6" experiment: v5 with the pending match
  *              bytes staged by cp.async ("depth" = "2".."4" iterations in flight); "v7": sequence table by one lane per
  *              chunk, then one lane per sequence (kernels_v7.cuh), forced for every chunk size up to 64 KiB; "default":
- *              v7 for chunks above 32 KiB up to 64 KiB, v5 otherwise.  Also sets the matching compressor.
+ *              v7 for chunks above 16 KiB up to 64 KiB, v5 otherwise.  Also sets the matching compressor ("v0" / "v1": their own,
+ *              "v2" .. "v7": v2, "default": default).
  *              The environment variable LZ4B200_KERNELS, read at lz4b200_create, is the same option.
  *   "team"     lanes per chunk for the team decoders: "4" / "8" / "16" / "32", "0" = by batch size (default)
- *   "compress" compressor generation: "v0" warp per chunk, "v1" one CTA per chunk, "v2" (default) two warp groups per CTA
+ *   "compress" compressor generation: "v0" warp per chunk, "v1" one CTA per chunk, "v2" two warp groups per CTA, "v3"
+ *              five stages on their own warps (kernels_c3.cuh; chunks up to 64 KiB at acceleration 1, the rest stays on v2),
+ *              "default": v3 for chunks of 16-64 KiB, v2 otherwise
  *   "accel"    LZ4_compress_fast's acceleration (lz4/lz4.c:1352-1375; the lz4fast levels of lzbench,
  *              _lzbench/compressors.cpp:348-356): 1 default, 2-3 probe every 2nd position, >= 4 every 4th
  *   "slices"   pipeline slices of the host entry points (0 = automatic); "ramp" = "0"/"1" small first slices when
  *              decompressing (default 1); "h2d" = "own"/"shared" stream for the inbound copies (default own)
  *   "host_register" = "1" page-locks caller buffers on first sight (what the lzbench wrappers turn on); a registered
  *              buffer must outlive the context or be released with lz4b200_unregister_host before it is freed
- *   "split"    v7: percent of a large batch decoded by the team decoder on a second stream ("0" default; measured slower)
+ *   "split"    v7: percent of a large batch decoded by the team decoder on a second stream ("0" default; measured slower);
+ *              "planes" = "8"/"16"/"32" chunks per warp in v7's table pass (default 32; measured: 16 the same, 8 slower)
  *   "timing" = "0"/"1" (see lz4b200_kernel_times_ms), "prof" = "0"/"1" (see lz4b200_debug_prof), "c1mode" (match-finder variant) */
 int lz4b200_set_option(lz4b200_ctx* ctx, const char* key, const char* value);
 

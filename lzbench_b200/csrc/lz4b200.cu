@@ -88,7 +88,8 @@ struct lz4b200_ctx {
     int device = 0;
     int sm_count = 148;
     int kernel_gen = 7;                 // decode: 7 = sequence table + one lane per sequence (kernels_v7.cuh; default for chunks <= 64 KiB, v5 otherwise and for the chunks v7 leaves to it); 0 warp per chunk, 1 CTA tile (TMA), 2 sub-warp teams, 3 + mapped lanes / pipelined match, 4 + warp-uniform fast path, 5 + compressed stream through a cp.async ring, long literal runs on the common path (default), 6 = 5 with cp.async-staged deep match pipeline (experiment)
-    int compress_gen = 2;               // compress: 0 warp per chunk, 1 CTA per chunk (parallel match finder + speculative parse), 2 = 1 with the phases on two warp groups (default)
+    int compress_gen = 3;               // compress: 0 warp per chunk, 1 CTA per chunk (parallel match finder + speculative parse), 2 = 1 with the phases on two warp groups,
+                                        // 3 (default) = kernels_c3.cuh for chunks of 16-64 KiB at acceleration 1 (five stages on their own warps), 2 for everything else
     int c1mode = 2;                     // compress: intra-warp candidate mode of the match finder (experiments; see kernels_c1.cuh)
     int v6depth = 2;                    // decode v6: iterations between fetching and storing a match part
     int accel = 1;                      // compress: LZ4_compress_fast's acceleration (1 = lz4 default; lz4fast levels), probe grid 1/2/4/8
@@ -107,7 +108,8 @@ struct lz4b200_ctx {
     cudaStream_t d2h_stream = nullptr;
     cudaStream_t aux_stream = nullptr;  // v7 decode: the team decoder's share of a large batch runs beside the sequence-table pass
     cudaEvent_t ev_fork[MAX_SLICES] = {}, ev_join[MAX_SLICES] = {};
-    int c3_workers = 8;                 // compress c3: worker warps per CTA beside the table warp (option "c3workers")
+    size_t c3_min_chunk = 16384;        // compress c3 pays from here on (a chunk costs 4 pipeline steps beside its tiles); "compress=v3" forces it
+    bool c3_forced = false;
     int v7_lanes = 32;                  // v7 pass 1: chunks per warp (option "planes")
     int split = -1;                     // percent of a large batch given to the team decoder (-1 = automatic, option "split")
     cudaStream_t h2d_stream = nullptr;  // ALL inbound bulk copies: spread over the compute streams they lose a third of the link (measured: 1 GiB each way in 32 ms on 8 streams, 22.6 ms on one)
@@ -295,7 +297,9 @@ int compress_slice(lz4b200_ctx* c, const u8* d_in, const u64* d_usz, size_t n, s
                               (u32)c->accel, c->c1mode));
         seg_stitch_size_kernel<<<gb, 256, 0, st>>>(sa, s.stage, slot_stride_for(SEG_BYTES), d_csz, (u32)n);
         c->launches += 5;
-    } else if (c->compress_gen == 3 && c->accel == 1 && c1_compress_supported(max_chunk)) {
+    } else if (c->compress_gen == 3 && c->accel == 1 && c1_compress_supported(max_chunk) && (max_chunk >= c->c3_min_chunk || c->c3_forced)) {
+        // measured (1 GiB, c2 vs c3, GB/s): mixed 4 KiB 75.7 / 72.5, 16 KiB 102.6 / 102.9, 32 KiB 106.4 / 107.9, 64 KiB 106.9 / 109.4;
+        // run-length data 4 KiB 62.8 / 60.5, 16 KiB 97 / 131, 32 KiB 102 / 177, 64 KiB 104 / 215; random 64 KiB 158 / 176
         CU(c3_launch_compress(d_in, s.uoff, d_usz, s.stage, stride, d_csz, (u32)n, s.ticket, c->sm_count, st,
                               c->prof_on ? (u64*)c->prof.p : nullptr));
         c->launches++;
@@ -660,15 +664,16 @@ int lz4b200_set_option(lz4b200_ctx* c, const char* key, const char* value)
         if (!strcmp(value, "v5")) { c->kernel_gen = 5; c->compress_gen = 2; return 0; }
         if (!strcmp(value, "v6")) { c->kernel_gen = 6; c->compress_gen = 2; return 0; }
         if (!strcmp(value, "v7") || !strcmp(value, "default")) {
-            c->kernel_gen = 7; c->compress_gen = 2; c->v7_min_chunk = strcmp(value, "v7") ? 16385 : 0;
+            c->kernel_gen = 7; c->compress_gen = strcmp(value, "v7") ? 3 : 2; c->c3_forced = false; c->v7_min_chunk = strcmp(value, "v7") ? 16385 : 0;
             return 0;
         }
     }
     if (!strcmp(key, "compress")) {
-        if (!strcmp(value, "v0")) { c->compress_gen = 0; return 0; }
-        if (!strcmp(value, "v1")) { c->compress_gen = 1; return 0; }
-        if (!strcmp(value, "v2")) { c->compress_gen = 2; return 0; }
-        if (!strcmp(value, "v3")) { c->compress_gen = 3; return 0; }
+        if (!strcmp(value, "v0")) { c->compress_gen = 0; c->c3_forced = false; return 0; }
+        if (!strcmp(value, "v1")) { c->compress_gen = 1; c->c3_forced = false; return 0; }
+        if (!strcmp(value, "v2")) { c->compress_gen = 2; c->c3_forced = false; return 0; }
+        if (!strcmp(value, "v3")) { c->compress_gen = 3; c->c3_forced = true; return 0; }
+        if (!strcmp(value, "default")) { c->compress_gen = 3; c->c3_forced = false; return 0; }
     }
     if (!strcmp(key, "c1mode")) { c->c1mode = atoi(value); return 0; }
     if (!strcmp(key, "accel")) {                        // LZ4_compress_fast's acceleration (lz4/lz4.c:1352-1375); the lz4fast levels of lzbench
@@ -688,7 +693,6 @@ int lz4b200_set_option(lz4b200_ctx* c, const char* key, const char* value)
         int p = atoi(value);
         if (p >= -1 && p <= 90) { c->split = p; return 0; }
     }
-    if (!strcmp(key, "c3workers")) { const int v = atoi(value); if (v == 8 || v == 12 || v == 16) { c->c3_workers = v; return 0; } return -1; }
     if (!strcmp(key, "planes")) { const int v = atoi(value); if (v == 8 || v == 16 || v == 32) { c->v7_lanes = v; return 0; } return -1; }
     if (!strcmp(key, "ramp")) { c->ramp = value[0] == '1'; return 0; }
     if (!strcmp(key, "h2d")) { c->own_h2d = strcmp(value, "shared") != 0; return 0; }
