@@ -243,6 +243,10 @@ compress_c3_kernel(const u8* __restrict__ in, const u64* __restrict__ in_off, co
                                 off[j] = ok ? p0 + j - c[j] : 0u;
                             }
                             *reinterpret_cast<uint2*>(hc + i0) = make_uint2(off[0] | (off[1] << 16), off[2] | (off[3] << 16));
+                            if (!__any_sync(FULL, (off[0] | off[1] | off[2] | off[3]) != 0)) {     // nothing matched in the slice (incompressible data)
+                                if ((lane & 7) == 0) okb[i0 >> 5] = 0;
+                                continue;
+                            }
                             u32 prev = __shfl_up_sync(FULL, off[3], 1);
                             if (lane == 0) prev = 0;                    // a slice starts a new run
                             u32 okn = 0, cn = 0;
