@@ -367,8 +367,8 @@ def run_b200(args):
     # dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full captures under profiles/
     # (profiles/README.md), valid for the default workload only (1 GiB mixed, 64 KiB chunks, default kernels)
     default_cfg = args.size_mib == 1024 and chunk == 65536 and args.corpus == "mixed" and not args.kernels
-    traffic = {"decompress": 3.4989e9 if default_cfg else None,          # profiles/r02_decompress_v7_ncu_raw.csv: table pass 0.41 + 0.48, lane-per-sequence pass 1.57 + 1.03 GB
-               "compress": 1.6951e9 if default_cfg else None}            # profiles/r01_final_compress_c2_ncu_raw.csv
+    traffic = {"decompress": 3.5969e9 if default_cfg else None,          # profiles/r02_decompress_v7_ncu_raw.csv: table pass 0.415 + 0.483, lane-per-sequence pass 1.662 + 1.037 GB
+               "compress": 1.6975e9 if default_cfg else None}            # profiles/r02_compress_c3_ncu_raw.csv: 1.076 + 0.621 GB
 
     def roof(kt, which):
         if not kt:
@@ -379,7 +379,8 @@ def run_b200(args):
                 "traffic": traffic[which], "kernel_ms": t * 1e3, "launches_timed": len(kt), "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": U + Cb,
                 "timed": ("parse_v7_kernel + order_v7_kernel + decompress_v7_kernel + decompress_v5_kernel (work list, empty here), one event pair"
-                          if which == "decompress" and not args.kernels and chunk > 32768 and chunk <= 65536 else "the codec kernel of the pass")}
+                          if which == "decompress" and not args.kernels and chunk > 16384 and chunk <= 65536 else
+                          "compress_c3_kernel" if which == "compress" and not args.kernels and 16384 <= chunk <= 65536 else "the codec kernel of the pass")}
 
     line = {
         "metric": "lz4_block_decompress_GBps_uncompressed",

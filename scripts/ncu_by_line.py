@@ -1,17 +1,19 @@
 """Aggregate the stall samples and executed instructions of one kernel in an .ncu-rep by CUDA source line.
 ncu's CSV source page is per SASS instruction; nvdisasm --print-line-info of the same build gives the line of every
 instruction, in the same order.
-usage: ncu_by_line.py <report.ncu-rep> <kernel symbol substring> [top N]   (run where the library was built)"""
+usage: ncu_by_line.py <report.ncu-rep> <kernel symbol substring>[:<substring of its mangled name>] [top N]   (run where the library was built)"""
 import collections, csv, io, os, re, subprocess, sys, tempfile
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 rep, sym = sys.argv[1], sys.argv[2]
+sec = sym                                   # "name:mangled" when the substring that picks the kernel in the report does not pick its ELF section
+if ":" in sym: sym, sec = sym.split(":", 1)
 top = int(sys.argv[3]) if len(sys.argv) > 3 else 40
 tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", os.path.join(ROOT, "lzbench_b200/_lib/liblz4b200.so")], cwd=tmp, check=True,
                stdout=subprocess.DEVNULL)
 cubin = max((os.path.join(tmp, f) for f in os.listdir(tmp)), key=os.path.getsize)
 lines = subprocess.run(["nvdisasm", "--print-line-info", cubin], capture_output=True, text=True).stdout.split("\n")
-start = next(i for i, l in enumerate(lines) if ".section" in l and ".text." in l and sym in l)
+start = next(i for i, l in enumerate(lines) if ".section" in l and ".text." in l and sec in l)
 end = next((i for i in range(start + 5, len(lines)) if ".section" in lines[i]), len(lines))
 cur, seq = None, []
 for l in lines[start:end]:
