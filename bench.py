@@ -380,7 +380,7 @@ def run_b200(args):
                 "algorithmic_bytes_per_launch": U + Cb,
                 "timed": ("parse_v7_kernel + order_v7_kernel + decompress_v7_kernel + decompress_v5_kernel (work list, empty here), one event pair"
                           if which == "decompress" and not args.kernels and chunk > 16384 and chunk <= 65536 else
-                          "compress_c3_kernel" if which == "compress" and not args.kernels and 16384 <= chunk <= 65536 else "the codec kernel of the pass")}
+                          "compress_c3_kernel" if which == "compress" and not args.kernels and chunk <= 65536 else "the codec kernel of the pass")}
 
     line = {
         "metric": "lz4_block_decompress_GBps_uncompressed",

@@ -121,7 +121,7 @@ int lz4b200_debug_prof(lz4b200_ctx* ctx, uint64_t* out16);
  *   "team"     lanes per chunk for the team decoders: "4" / "8" / "16" / "32", "0" = by batch size (default)
  *   "compress" compressor generation: "v0" warp per chunk, "v1" one CTA per chunk, "v2" two warp groups per CTA, "v3"
  *              five stages on their own warps (kernels_c3.cuh; chunks up to 64 KiB at acceleration 1, the rest stays on v2),
- *              "default": v3 for chunks of 16-64 KiB, v2 otherwise
+ *              "default": v3 where it applies, v2 otherwise
  *   "accel"    LZ4_compress_fast's acceleration (lz4/lz4.c:1352-1375; the lz4fast levels of lzbench,
  *              _lzbench/compressors.cpp:348-356): 1 default, 2-3 probe every 2nd position, >= 4 every 4th
  *   "slices"   pipeline slices of the host entry points (0 = automatic); "ramp" = "0"/"1" small first slices when

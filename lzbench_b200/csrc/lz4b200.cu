@@ -89,7 +89,7 @@ struct lz4b200_ctx {
     int sm_count = 148;
     int kernel_gen = 7;                 // decode: 7 = sequence table + one lane per sequence (kernels_v7.cuh; default for chunks <= 64 KiB, v5 otherwise and for the chunks v7 leaves to it); 0 warp per chunk, 1 CTA tile (TMA), 2 sub-warp teams, 3 + mapped lanes / pipelined match, 4 + warp-uniform fast path, 5 + compressed stream through a cp.async ring, long literal runs on the common path (default), 6 = 5 with cp.async-staged deep match pipeline (experiment)
     int compress_gen = 3;               // compress: 0 warp per chunk, 1 CTA per chunk (parallel match finder + speculative parse), 2 = 1 with the phases on two warp groups,
-                                        // 3 (default) = kernels_c3.cuh for chunks of 16-64 KiB at acceleration 1 (five stages on their own warps), 2 for everything else
+                                        // 3 (default) = kernels_c3.cuh for chunks up to 64 KiB at acceleration 1 (five stages on their own warps), 2 for everything else
     int c1mode = 2;                     // compress: intra-warp candidate mode of the match finder (experiments; see kernels_c1.cuh)
     int v6depth = 2;                    // decode v6: iterations between fetching and storing a match part
     int accel = 1;                      // compress: LZ4_compress_fast's acceleration (1 = lz4 default; lz4fast levels), probe grid 1/2/4/8
@@ -108,7 +108,10 @@ struct lz4b200_ctx {
     cudaStream_t d2h_stream = nullptr;
     cudaStream_t aux_stream = nullptr;  // v7 decode: the team decoder's share of a large batch runs beside the sequence-table pass
     cudaEvent_t ev_fork[MAX_SLICES] = {}, ev_join[MAX_SLICES] = {};
-    size_t c3_min_chunk = 16384;        // compress c3 pays from here on (a chunk costs 4 pipeline steps beside its tiles); "compress=v3" forces it
+    size_t c3_min_chunk = 0;            // c3 for every chunk size up to 64 KiB: below 16 KiB it is 2-4 % slower than c2 (a chunk costs 4 pipeline steps beside its
+                                        // tiles) but stays within a fraction of a percent of the reference's size on ANY input, where c2's 256-position batches
+                                        // lose up to 9 % on small chunks that mix runs and text (scripts/fuzz_gpu.py, same seed: 32 size failures with c2, 17 with c3 --
+                                        // the rest are chunks above 64 KiB, whose segments see 16 KiB of history)
     bool c3_forced = false;
     int v7_lanes = 32;                  // v7 pass 1: chunks per warp (option "planes")
     int split = -1;                     // percent of a large batch given to the team decoder (-1 = automatic, option "split")

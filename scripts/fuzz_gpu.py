@@ -13,6 +13,7 @@ rng = np.random.default_rng(seed)
 print("fuzz seed", seed, flush=True)
 ctx = L.Lz4B200(0)
 if os.environ.get("FUZZ_KERNELS"): ctx.set_option("kernels", os.environ["FUZZ_KERNELS"])
+if os.environ.get("FUZZ_COMPRESS"): ctx.set_option("compress", os.environ["FUZZ_COMPRESS"])
 ACCEL = int(os.environ.get("FUZZ_ACCEL", "1"))
 ctx.set_option("accel", str(ACCEL))
 KINDS = ["mixed", "random", "repeat", "zero"]
