@@ -18,6 +18,7 @@
 #include "kernels_c1.cuh"
 #include "kernels_c2.cuh"
 #include "kernels_c3.cuh"
+#include "kernels_coarse.cuh"
 #include "segmented.cuh"
 #include "frame.cuh"
 #include "staging.cuh"
@@ -132,6 +133,10 @@ struct lz4b200_ctx {
     bool prof_on = false;
     DevBuf stage;                       // compress: n_chunks slots of slot_stride bytes (or one slot per 64 KiB segment)
     DevBuf seg64, seg32;                // segmented compress (segmented.cuh): u64 / u32 job arrays
+    DevBuf coarse;                      // coarse decode (kernels_coarse.cuh): list counters per slice, descriptors, descriptor counts, work list
+    size_t coarse_chunks = 0;           // chunk count its arrays are laid out for (current call; 0: not available)
+    bool coarse_on = true;              // option "coarse"
+    cudaEvent_t ev_coarse = nullptr;    // the last coarse copy kernel of this context (they run one at a time)
     DevBuf v7_table, v7_u32;            // v7 decode: sequence table (u64 entries) and nseq / route / team list (u32[3][n_chunks])
     size_t v7_chunks = 0;               // chunk count the u32 arrays are laid out for (current call)
     size_t v7_table_chunks = 0;         // chunks the table has room for (current call): all of a host call's, one sub-batch of a device call's
@@ -227,6 +232,15 @@ void ensure_v7(lz4b200_ctx* c, size_t n, size_t table_chunks, size_t max_chunk)
     if (c->v7_u32.ensure((4 * n + V7_ZERO_WORDS * lz4b200_ctx::MAX_SLICES) * sizeof(u32)) != cudaSuccess ||
         c->v7_table.ensure(table_chunks * c->v7_per_chunk * sizeof(u64)) != cudaSuccess) { cudaGetLastError(); return; }
     c->v7_chunks = n; c->v7_table_chunks = table_chunks;
+}
+
+// coarse decode scratch for n chunks (chunks above 64 KiB only).  Failing to get the memory is not an error.
+void ensure_coarse(lz4b200_ctx* c, size_t n, size_t max_chunk)
+{
+    c->coarse_chunks = 0;
+    if (!c->coarse_on || c->kernel_gen < 5 || max_chunk <= V7_MAX_CHUNK || n == 0) return;
+    if (c->coarse.ensure(1024 + n * (C_MAXD * sizeof(uint4) + 2 * sizeof(u32))) != cudaSuccess) { cudaGetLastError(); return; }
+    c->coarse_chunks = n;
 }
 
 Scratch scratch_at(lz4b200_ctx* c, size_t first_chunk, size_t stride, int slice)
@@ -414,6 +428,25 @@ int decompress_slice(lz4b200_ctx* c, const u8* d_in, const u64* d_csz, const u64
             }
             if (mA) CU(cudaStreamWaitEvent(st, c->ev_join[s.slice], 0));
         }
+    } else if (c->kernel_gen >= 7 && c->coarse_chunks && cap_all == 0 && max_chunk > V7_MAX_CHUNK && s.first_chunk + n <= c->coarse_chunks) {
+        // large chunks: the ones that are a handful of long copies are cut into 32 KiB pieces (kernels_coarse.cuh), the team
+        // decoder takes the rest from a list
+        u8* b = (u8*)c->coarse.p;
+        const size_t nt = c->coarse_chunks;
+        CoarseParams P{ d_in, s.coff, d_csz, s.uoff, d_usz, d_out, s.status, (u32)n,
+                        (uint4*)(b + 1024) + s.first_chunk * C_MAXD,
+                        (u32*)(b + 1024 + nt * C_MAXD * sizeof(uint4)) + s.first_chunk,
+                        (u32*)(b + 1024 + nt * C_MAXD * sizeof(uint4)) + nt + s.first_chunk,
+                        (u32*)b + s.slice, (u32*)b + 64 + 2 * s.slice };
+        // the copy kernel synchronises its CTAs through a counter, so all of them must be resident: two of them on two
+        // streams (pipeline slices) could each hold the slots the other waits for -- one at a time per context
+        if (!c->ev_coarse) CU(cudaEventCreateWithFlags(&c->ev_coarse, cudaEventDisableTiming));
+        else CU(cudaStreamWaitEvent(st, c->ev_coarse, 0));
+        CU(coarse_launch(P, c->sm_count, st));
+        CU(cudaEventRecord(c->ev_coarse, st));
+        CU(v5_launch_decompress(team == 32 ? 16 : team, d_in, s.coff, d_csz, s.uoff, d_usz, d_out, s.status, d_bad, (u32)n,
+                                s.ticket, c->sm_count, st, cap_all, P.list, P.list_count));
+        c->launches += 3;
     } else if (c->kernel_gen >= 7) {
         CU(v5_launch_decompress(team == 32 ? 16 : team, d_in, s.coff, d_csz, s.uoff, d_usz, d_out, s.status, d_bad, (u32)n,
                                 s.ticket, c->sm_count, st, cap_all));
@@ -613,6 +646,7 @@ void lz4b200_destroy(lz4b200_ctx* c)
     if (c->aux_stream) cudaStreamDestroy(c->aux_stream);
     if (c->h2d_stream) cudaStreamDestroy(c->h2d_stream);
     if (c->ev_sizes) cudaEventDestroy(c->ev_sizes);
+    if (c->ev_coarse) cudaEventDestroy(c->ev_coarse);
     for (int i = 0; i < lz4b200_ctx::MAX_SLICES; i++) {
         if (c->ev_scan[i]) cudaEventDestroy(c->ev_scan[i]);
         if (c->ev_done[i]) cudaEventDestroy(c->ev_done[i]);
@@ -696,6 +730,7 @@ int lz4b200_set_option(lz4b200_ctx* c, const char* key, const char* value)
         int p = atoi(value);
         if (p >= -1 && p <= 90) { c->split = p; return 0; }
     }
+    if (!strcmp(key, "coarse")) { c->coarse_on = value[0] == '1'; return 0; }
     if (!strcmp(key, "planes")) { const int v = atoi(value); if (v == 8 || v == 16 || v == 32) { c->v7_lanes = v; return 0; } return -1; }
     if (!strcmp(key, "ramp")) { c->ramp = value[0] == '1'; return 0; }
     if (!strcmp(key, "h2d")) { c->own_h2d = strcmp(value, "shared") != 0; return 0; }
@@ -760,6 +795,7 @@ int lz4b200_decompress_device(lz4b200_ctx* c, const void* d_in, const uint64_t* 
     CU(cudaSetDevice(c->device));
     if (int rc = ensure_scratch(c, n ? n : 1, 0)) return rc;
     ensure_v7(c, n, std::min(n, V7_SUB), max_chunk);
+    ensure_coarse(c, n, max_chunk);
     u32* bad = d_bad_chunks ? d_bad_chunks : (u32*)((u8*)c->scalars.p + SC_BAD);
     CU(cudaMemsetAsync(bad, 0, sizeof(u32), st));
     if (n == 0) return 0;
@@ -881,6 +917,7 @@ int64_t lz4b200_decompress_batch(lz4b200_ctx* c, const char* in, const size_t* c
     CU(c->d_packed.ensure(ctotal + 16));
     if (int rc = ensure_scratch(c, n, 0)) return rc;
     ensure_v7(c, n, n, max_chunk);
+    ensure_coarse(c, n, max_chunk);
     size_t first[lz4b200_ctx::MAX_SLICES + 1];
     const int K = plan_slices(c, chunk_sizes, n, total, true, first);
     if (int rc = ensure_events(c, K)) return rc;

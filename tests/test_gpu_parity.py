@@ -217,6 +217,80 @@ def test_corrupted_blocks_never_crash_and_match_oracle(gpu_ctx, kernels):
             assert np.array_equal(out[i], ref_out), i
 
 
+def _coarse_corpus(rng):
+    """Large chunks that are a handful of long copies -- what kernels_coarse.cuh takes -- beside chunks it must leave alone."""
+    n = 1 << 18
+    rnd = rng.integers(0, 256, n, dtype=np.uint8)
+    zero = np.zeros(n, dtype=np.uint8)
+    per = np.tile(rng.integers(0, 256, 300, dtype=np.uint8), n // 300 + 1)[:n]
+    half = np.concatenate([rnd[:n // 2], zero[:n // 2]])                 # one long literal run, then one long match
+    back = np.concatenate([rnd[:100000], rnd[40000:100000], np.zeros(n - 160000, dtype=np.uint8)])   # a far match of 60 000 bytes
+    text = L.corpus("mixed", n, seed=21)                                 # thousands of sequences: not for this path
+    return [rnd, zero, per, half, back, text]
+
+
+@pytest.mark.parametrize("coarse", ["1", "0"])
+def test_coarse_chunks_decode_bit_exact(gpu_ctx, coarse):
+    """Chunks above 64 KiB made of few long copies (incompressible, run-length, short-period, raw-stored), compressed by the
+    reference (one match per run) and by this library (one match per 48 KiB segment): bit-exact with and without the coarse path."""
+    gpu_ctx.set_option("coarse", coarse)
+    try:
+        rng = np.random.default_rng(31)
+        parts = _coarse_corpus(rng)
+        data = np.concatenate(parts)
+        cs = np.asarray([len(p) for p in parts], dtype=np.uint64)
+        for packed, compr in (O.oracle_chunked_compress(data, cs), gpu_ctx.compress_batch(data, cs)[:2]):
+            total = int(np.asarray(compr).sum())
+            out, r = gpu_ctx.decompress_batch(packed[:total], compr, cs)
+            assert r == len(data) and np.array_equal(out, data)
+        # one of them stored raw (compr == size), and a ragged list around the 64 KiB limit of the path
+        packed, compr = O.oracle_chunked_compress(data, cs)
+        blocks = list(O.split_chunks(packed, compr))
+        blocks[1] = parts[1]; compr = compr.copy(); compr[1] = len(parts[1])
+        out, r = gpu_ctx.decompress_batch(np.concatenate(blocks), compr, cs)
+        assert r == len(data) and np.array_equal(out, data)
+        sizes = np.asarray([65535, 65536, 65537, 70000, 200000, 13, 1 << 20, 4 << 20], dtype=np.uint64)
+        for kind, seed in (("random", 4), ("zero", 5), ("repeat", 5)):
+            d2 = L.corpus(kind, int(sizes.sum()), seed=seed)
+            for packed, compr in (O.oracle_chunked_compress(d2, sizes), gpu_ctx.compress_batch(d2, sizes)[:2]):
+                total = int(np.asarray(compr).sum())
+                out, r = gpu_ctx.decompress_batch(packed[:total], compr, sizes)
+                assert r == len(d2) and np.array_equal(out, d2), kind
+    finally:
+        gpu_ctx.set_option("coarse", "1")
+
+
+def test_coarse_chunks_corrupted_same_verdict_as_oracle(gpu_ctx):
+    """Damaged blocks of the kind the coarse path takes: the same accept / reject decision as the oracle, and the oracle's
+    bytes where it accepts (the coarse scan only ever accepts what passes every rule; the rest goes to the team decoder)."""
+    rng = np.random.default_rng(37)
+    n = 1 << 17
+    sources = [rng.integers(0, 256, n, dtype=np.uint8), np.zeros(n, dtype=np.uint8),
+               np.concatenate([rng.integers(0, 256, n // 2, dtype=np.uint8), np.zeros(n // 2, dtype=np.uint8)])]
+    for data in sources:
+        good = O.oracle_compress(data)
+        blocks, expect = [], []
+        for i in range(96):
+            bad = good.copy()
+            for _ in range(int(rng.integers(1, 3))):
+                # the first bytes (token, length bytes, offset) and the last ones decide most; the rest of a literal run does not
+                where = int(rng.integers(0, min(600, len(bad)))) if i % 3 else int(rng.integers(max(0, len(bad) - 600), len(bad)))
+                bad[where] = int(rng.integers(0, 256))
+            blocks.append(bad)
+            r, out = O.oracle_decompress(bad, n)
+            expect.append((r == n, out))
+        packed = np.concatenate(blocks)
+        compr = np.full(len(blocks), len(good), dtype=np.uint64)
+        cs = np.full(len(blocks), n, dtype=np.uint64)
+        out, r = gpu_ctx.decompress_batch(packed, compr, cs)
+        n_bad = sum(1 for ok, _ in expect if not ok)
+        assert (r == -n_bad) if n_bad else (r == n * len(blocks))
+        out = out.reshape(len(blocks), n)
+        for i, (ok, ref_out) in enumerate(expect):
+            if ok:
+                assert np.array_equal(out[i], ref_out), i
+
+
 @pytest.mark.parametrize("kernels", ["v0", "v1", "v2", "v3", "v4", "v5", "v6", "v7"])
 def test_plugin_signature_wrappers(gpu_ctx, kernels):
     """lzbench_lz4_b200_{init,compress,decompress,deinit}: the unpatched-harness path, one chunk per call."""
