@@ -26,8 +26,8 @@
 //   E  emit (4 warps, tile k-4), one lane per sequence: backward extension (lz4/lz4.c:1019), sizes, scan, bytes
 //      (lz4/lz4.c:1022-1135).
 //
-// Same block format rules as c1/c2 (end-of-block rules lz4/lz4.c:883-884, last literals :1204-1231); chunks above
-// 64 KiB and the lz4fast levels stay on c2.
+// Same block format rules as c1/c2 (end-of-block rules lz4/lz4.c:883-884, last literals :1204-1231).  Chunks above 64 KiB
+// come as jobs of 16 KiB history + 48 KiB new data (segmented.cuh); the lz4fast levels stay on c2.
 #pragma once
 #include "common.cuh"
 #include "kernels_c1.cuh"
@@ -122,9 +122,14 @@ __device__ __forceinline__ u32 c3_warp_count16(const u8* s_in, u32 a, u32 o, u32
 template <bool PROF>                             // PROF: per-stage cycle counters (scripts/gpu_probe.py PROF=1); the production instance carries none
 __global__ void __launch_bounds__(C3_THREADS, 2)
 compress_c3_kernel(const u8* __restrict__ in, const u64* __restrict__ in_off, const u64* __restrict__ usz,
-                   u8* __restrict__ stage, u64 slot_stride, u64* __restrict__ csz, u32 n_chunks, u32* ticket,
-                   u64* __restrict__ prof_arg)
+                   u8* __restrict__ stage, u64 slot_stride, u64* __restrict__ csz, u32 n_chunks_arg, u32* ticket,
+                   u64* __restrict__ prof_arg, const u64* __restrict__ n_dev, u32* __restrict__ tail_pos, u32* __restrict__ tail_len,
+                   const u32* __restrict__ hist_arr)
 {
+    // segmented mode (segmented.cuh, chunks above 64 KiB): the job count lives in device memory, a job starts with `hist` bytes of
+    // history (hashed and matchable, not encoded), a job that is not the end of its chunk is exempt from the end-of-block rules,
+    // and every job reports where its last literals start and how many they are
+    const u32 n_chunks = n_dev ? (u32)*n_dev : n_chunks_arg;
     typedef C3Smem S;
     u64* const prof = PROF ? prof_arg : nullptr;
     extern __shared__ __align__(128) u8 smem[];
@@ -192,13 +197,15 @@ compress_c3_kernel(const u8* __restrict__ in, const u64* __restrict__ in_off, co
             uint4* t4 = reinterpret_cast<uint4*>(s_tab);
             for (u32 i = ltid; i < (2u << C1_HBITS) / 16; i += C3_LIVE) t4[i] = make_uint4(0, 0, 0, 0);
         }
-        if (tid == 0) { s_misc[1] = 0; s_misc[3] = 0; s_misc[5] = 0; s_misc[6] = 0; }
+        const u32 hist = hist_arr ? (hist_arr[chunk] & 0x7FFFFFFFu) : 0u;     // the chain starts behind the history
+        const bool inner = hist_arr && (hist_arr[chunk] >> 31);
+        if (tid == 0) { s_misc[1] = 0; s_misc[3] = hist; s_misc[5] = hist; s_misc[6] = 0; }
         __syncthreads();
         if (prof && tid == 0) atomicAdd((unsigned long long*)&prof[5], (unsigned long long)(clock64() - pt0));
 
         if (n >= MIN_LENGTH) {
-            const u32 mfl = n - MFLIMIT;              // last position a match may start at
-            const u32 mlimit = n - LASTLITERALS;      // matches end at or before this
+            const u32 mfl = n - (inner ? MINMATCH : MFLIMIT);     // last position a match may start at (lz4/lz4.c:883-884 bind only the real end of a block)
+            const u32 mlimit = n - (inner ? 0u : LASTLITERALS);   // matches end at or before this
             const u32 n_tiles = mfl / C3_TILE + 1;
             const u32* const s_in32 = reinterpret_cast<const u32*>(s_in);
             u32 cur = 0;                              // P, E: chain state = end of the last match (= literal anchor)
@@ -367,10 +374,10 @@ compress_c3_kernel(const u8* __restrict__ in, const u64* __restrict__ in_off, co
                         // the end of a long match that starts at p: remembered, else measured by the whole warp (uniform p)
                         auto long_end = [&](u32 p) -> u32 {
                             const u32 nl = *nlongm;
-                            for (u32 i = 0; i < nl; i++) if (longm[i] == p) return longm[C3_NLONGM + i];
+                            for (u32 i = 0; i < nl; i++) if (longm[i] == p) return (u32)longm[C3_NLONGM + i] + 1u;
                             const u32 o = hc[p - t0];
                             const u32 e = p + c3_warp_count16(s_in, p, o, 144, mlimit, lane);               // (a long one: at least 148 bytes are known to be equal)
-                            if (lane == 0 && nl < C3_NLONGM) { longm[nl] = (u16)p; longm[C3_NLONGM + nl] = (u16)e; *nlongm = nl + 1; }
+                            if (lane == 0 && nl < C3_NLONGM) { longm[nl] = (u16)p; longm[C3_NLONGM + nl] = (u16)(e - 1u); *nlongm = nl + 1; }
                             __syncwarp();
                             return e;
                         };
@@ -468,7 +475,7 @@ compress_c3_kernel(const u8* __restrict__ in, const u64* __restrict__ in_off, co
                         for (u32 sb = sel; sb; sb &= sb - 1u) {
                             const u32 idx = (u32)__ffs(sb) - 1u, p = ws + idx;
                             const u32 ml = mlw[idx];
-                            seq[base] = (u16)p; seq[C3_MAXSEQ + base] = (u16)(p + ml); seq[2 * C3_MAXSEQ + base] = hc[p - t0];
+                            seq[base] = (u16)p; seq[C3_MAXSEQ + base] = (u16)(p + ml - 1u); seq[2 * C3_MAXSEQ + base] = hc[p - t0];   // (ends are stored less 1: a job inside a chunk may match up to position 65 536)
                             if (ml == C3_LONG) myl = base;
                             base++;
                         }
@@ -478,7 +485,7 @@ compress_c3_kernel(const u8* __restrict__ in, const u64* __restrict__ in_off, co
                             const int sl = __ffs(lm) - 1; lm &= lm - 1;
                             const u32 j = __shfl_sync(FULL, myl, sl);
                             const u32 e = long_end(seq[j]);
-                            if (lane == 0) seq[C3_MAXSEQ + j] = (u16)e;
+                            if (lane == 0) seq[C3_MAXSEQ + j] = (u16)(e - 1u);
                         }
                         if (half && lane == 0) {
                             s_hdr[(t & 1) * 2] = seq_base + nseq; s_hdr[(t & 1) * 2 + 1] = cur_tile;
@@ -509,8 +516,8 @@ compress_c3_kernel(const u8* __restrict__ in, const u64* __restrict__ in_off, co
                             u32 enc = 0;
                             if (j < nseq) {
                                 u32 p = seq[j];
-                                const u32 e = seq[C3_MAXSEQ + j], o = seq[2 * C3_MAXSEQ + j];
-                                const u32 anchor = j ? (u32)seq[C3_MAXSEQ + j - 1] : cur;
+                                const u32 e = (u32)seq[C3_MAXSEQ + j] + 1u, o = seq[2 * C3_MAXSEQ + j];
+                                const u32 anchor = j ? (u32)seq[C3_MAXSEQ + j - 1] + 1u : cur;
                                 while (p > anchor && p > o && s_in[p - 1] == s_in[p - o - 1]) p--;      // lz4/lz4.c:1019
                                 const u32 lit = p - anchor, ml = e - p - MINMATCH;
                                 enc = 1 + c1_len_ext_bytes(lit) + lit + 2 + c1_len_ext_bytes(ml);
@@ -532,8 +539,8 @@ compress_c3_kernel(const u8* __restrict__ in, const u64* __restrict__ in_off, co
                             u32 before = 0;
                             for (u32 q = 0; q < b; q++) before += s_blk[q];
                             if (j < nseq) {
-                                const u32 p = s_seqq[j], e = seq[C3_MAXSEQ + j], o = seq[2 * C3_MAXSEQ + j];
-                                const u32 anchor = j ? (u32)seq[C3_MAXSEQ + j - 1] : cur;
+                                const u32 p = s_seqq[j], e = (u32)seq[C3_MAXSEQ + j] + 1u, o = seq[2 * C3_MAXSEQ + j];
+                                const u32 anchor = j ? (u32)seq[C3_MAXSEQ + j - 1] + 1u : cur;
                                 const u32 lit = p - anchor, ml = e - p - MINMATCH;
                                 u8* q = dst + op + before + s_seqo[j];
                                 *q++ = (u8)(((lit < RUN_MASK ? lit : RUN_MASK) << 4) | (ml < ML_MASK ? ml : ML_MASK));
@@ -579,6 +586,7 @@ compress_c3_kernel(const u8* __restrict__ in, const u64* __restrict__ in_off, co
                 if (last >= RUN_MASK) c1_put_ext(o + 1, last - RUN_MASK);
             }
             for (u32 i = ltid; i < last; i += C3_LIVE) o[hdr + i] = s_in[cur + i];
+            if (tid == 0 && tail_pos) { tail_pos[chunk] = op; tail_len[chunk] = last; }
             op += hdr + last;
             if (tid == 0) csz[chunk] = op;
         }
@@ -587,7 +595,8 @@ compress_c3_kernel(const u8* __restrict__ in, const u64* __restrict__ in_off, co
 }
 
 inline cudaError_t c3_launch_compress(const u8* in, const u64* in_off, const u64* usz, u8* stage, u64 stride, u64* csz,
-                                      u32 n, u32* ticket, int sm_count, cudaStream_t st, u64* prof = nullptr)
+                                      u32 n, u32* ticket, int sm_count, cudaStream_t st, u64* prof = nullptr, const u64* n_dev = nullptr,
+                                      u32* tail_pos = nullptr, u32* tail_len = nullptr, const u32* hist = nullptr)
 {
     cudaError_t e = cudaFuncSetAttribute(compress_c3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C3Smem::BYTES);   // per device: every launch
     if (e == cudaSuccess && prof) e = cudaFuncSetAttribute(compress_c3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C3Smem::BYTES);
@@ -596,8 +605,8 @@ inline cudaError_t c3_launch_compress(const u8* in, const u64* in_off, const u64
     if (grid > n) grid = n;
     e = cudaMemsetAsync(ticket, 0, sizeof(u32), st);
     if (e != cudaSuccess) return e;
-    if (prof) compress_c3_kernel<true><<<grid, C3_THREADS, C3Smem::BYTES, st>>>(in, in_off, usz, stage, stride, csz, n, ticket, prof);
-    else compress_c3_kernel<false><<<grid, C3_THREADS, C3Smem::BYTES, st>>>(in, in_off, usz, stage, stride, csz, n, ticket, nullptr);
+    if (prof) compress_c3_kernel<true><<<grid, C3_THREADS, C3Smem::BYTES, st>>>(in, in_off, usz, stage, stride, csz, n, ticket, prof, n_dev, tail_pos, tail_len, hist);
+    else compress_c3_kernel<false><<<grid, C3_THREADS, C3Smem::BYTES, st>>>(in, in_off, usz, stage, stride, csz, n, ticket, nullptr, n_dev, tail_pos, tail_len, hist);
     return cudaGetLastError();
 }
 

@@ -309,6 +309,10 @@ int compress_slice(lz4b200_ctx* c, const u8* d_in, const u64* d_usz, size_t n, s
         ScanJob js{ sa.jobs_per_chunk, sa.job_base, sa.n_jobs, nullptr };
         scan_sizes_kernel<<<1, SCAN_THREADS, 0, st>>>(js, none, (u64)n);
         seg_fill_kernel<<<gb, 256, 0, st>>>(d_usz, s.uoff, sa, (u32)n);
+        if (c->compress_gen == 3 && c->accel == 1)
+            CU(c3_launch_compress(d_in, sa.job_in_off, sa.job_len, s.stage, slot_stride_for(SEG_BYTES), sa.job_csz,
+                                  (u32)jobs_max, s.ticket, c->sm_count, st, nullptr, sa.n_jobs, sa.job_tail_pos, sa.job_tail_len, sa.job_hist));
+        else
         CU(c2_launch_compress(d_in, sa.job_in_off, sa.job_len, s.stage, slot_stride_for(SEG_BYTES), sa.job_csz,
                               (u32)jobs_max, s.ticket, c->sm_count, st, sa.n_jobs, sa.job_tail_pos, sa.job_tail_len, sa.job_hist, nullptr,
                               (u32)c->accel, c->c1mode));
