@@ -30,6 +30,7 @@ constexpr u32 C_SCAN_WARPS = 4;
 struct CoarseParams {
     const u8* in; const u64* in_off; const u64* csz; const u64* out_off; const u64* usz; u8* out;
     u32* status; u32 n_chunks;
+    u32 cap_all;                                   // see V5Params::cap_all (frames: the end-of-block rules are checked against the frame's block size)
     uint4* desc;                                   // [n_chunks][C_MAXD]: x position in the chunk, y stream position (literals) / offset (match), z length, w bit 0: match, bits 8..: level
     u32* ndesc;                                    // descriptors of the chunk (0: not taken)
     u32* list; u32* list_count;                    // chunks left to the team decoder
@@ -81,6 +82,7 @@ coarse_scan_kernel(const __grid_constant__ CoarseParams P)
     } else if (n64 >= 65536 && n64 < 0x7F000000ull && clen64 >= 16 && clen64 < 0x7F000000ull &&
                (clen64 * 85 < n64 || clen64 + (n64 >> 5) >= n64)) {          // few sequences: fewer than n / 256, or hardly compressed
         const u32 clen = (u32)clen64, n = (u32)n64;
+        const u32 capv = P.cap_all > n ? P.cap_all : n;
         u32 ip = 0, op = 0;
         take = true;
         while (take) {
@@ -93,7 +95,7 @@ coarse_scan_kernel(const __grid_constant__ CoarseParams P)
             if (len > n) { take = false; break; }
             const u32 L = (u32)len, cpy = op + L;
             if (cpy > n || (u64)ip + L > clen) { take = false; break; }
-            const bool last = cpy + MFLIMIT > n || (u64)ip + L + (2 + 1 + LASTLITERALS) > clen;
+            const bool last = cpy + MFLIMIT > capv || (u64)ip + L + (2 + 1 + LASTLITERALS) > clen;
             if (L) { if (lane == 0) d[nd] = make_uint4(op, ip, L, 0u); nd++; }
             if (last) {
                 if (ip + L != clen || cpy != n) take = false;                // (the team decoder names the rule)
@@ -107,7 +109,7 @@ coarse_scan_kernel(const __grid_constant__ CoarseParams P)
                 if (!coarse_read_length(src, clen, ip, m, lane) || ip + LASTLITERALS - 1 >= clen) { take = false; break; }
             }
             m += MINMATCH;
-            if (m > n || cpy + (u32)m + LASTLITERALS > n || off == 0 || off > cpy) { take = false; break; }
+            if (m > n || cpy + (u32)m + LASTLITERALS > capv || cpy + (u32)m > n || off == 0 || off > cpy) { take = false; break; }
             // level: one above the highest earlier match whose output the source [cpy - off, cpy - off + min(off, m)) touches
             const u32 s0 = cpy - off, s1 = s0 + (off < (u32)m ? off : (u32)m);
             u32 lvl = 0;
@@ -153,7 +155,7 @@ __device__ __forceinline__ void coarse_grid_barrier(u32* counter, u32& round)
 __global__ void __launch_bounds__(C_COPY_THREADS)
 coarse_copy_kernel(const __grid_constant__ CoarseParams P)
 {
-    __shared__ u32 s_pick[C_MAXD], s_npick;
+    __shared__ u32 s_mask[C_MAXD / 32];                 // descriptors of the current level (in descriptor order: the CTAs that share a chunk number its pieces alike)
     const u32 G = gridDim.x, b = blockIdx.x, tid = threadIdx.x;
     const u32 levels = *reinterpret_cast<volatile u32*>(P.max_level) + 1;
     u32 round = 0;
@@ -166,14 +168,15 @@ coarse_copy_kernel(const __grid_constant__ CoarseParams P)
                 const u32 mine = G > P.n_chunks ? b / P.n_chunks : 0;
                 const uint4* const dsc = P.desc + (size_t)c * C_MAXD;
                 // the descriptors of this level, in order (one thread each looks at its descriptor)
-                if (tid == 0) s_npick = 0;
+                {
+                    const unsigned bal = __ballot_sync(FULL, tid < nd && (dsc[tid < nd ? tid : 0].w >> 8) == lv);
+                    if ((tid & 31) == 0) s_mask[tid >> 5] = bal;
+                }
                 __syncthreads();
-                if (tid < nd && (dsc[tid].w >> 8) == lv) s_pick[atomicAdd(&s_npick, 1u)] = tid;
-                __syncthreads();
-                const u32 np = s_npick;
                 u32 piece = 0;                                             // running piece number over the level's descriptors of the chunk
-                for (u32 k = 0; k < np; k++) {
-                    const uint4 q = dsc[s_pick[k]];
+                for (u32 k = 0; k < nd; k++) {
+                    if (!((s_mask[k >> 5] >> (k & 31)) & 1u)) continue;
+                    const uint4 q = dsc[k];
                     u8* const dst = P.out + P.out_off[c] + q.x;
                     for (u64 a = 0; a < q.z; a += C_PIECE, piece++) {
                         if (piece % share != mine) continue;

@@ -432,12 +432,12 @@ int decompress_slice(lz4b200_ctx* c, const u8* d_in, const u64* d_csz, const u64
             }
             if (mA) CU(cudaStreamWaitEvent(st, c->ev_join[s.slice], 0));
         }
-    } else if (c->kernel_gen >= 7 && c->coarse_chunks && cap_all == 0 && max_chunk > V7_MAX_CHUNK && s.first_chunk + n <= c->coarse_chunks) {
+    } else if (c->kernel_gen >= 7 && c->coarse_chunks && max_chunk > V7_MAX_CHUNK && s.first_chunk + n <= c->coarse_chunks) {
         // large chunks: the ones that are a handful of long copies are cut into 32 KiB pieces (kernels_coarse.cuh), the team
         // decoder takes the rest from a list
         u8* b = (u8*)c->coarse.p;
         const size_t nt = c->coarse_chunks;
-        CoarseParams P{ d_in, s.coff, d_csz, s.uoff, d_usz, d_out, s.status, (u32)n,
+        CoarseParams P{ d_in, s.coff, d_csz, s.uoff, d_usz, d_out, s.status, (u32)n, cap_all,
                         (uint4*)(b + 1024) + s.first_chunk * C_MAXD,
                         (u32*)(b + 1024 + nt * C_MAXD * sizeof(uint4)) + s.first_chunk,
                         (u32*)(b + 1024 + nt * C_MAXD * sizeof(uint4)) + nt + s.first_chunk,
@@ -1087,6 +1087,7 @@ int64_t lz4b200_frame_decompress(lz4b200_ctx* c, const char* in, size_t in_size,
     CU(c->d_plain.ensure(limit + 16));
     if (int rc = ensure_scratch(c, n, 0)) return rc;
     ensure_v7(c, n, n, fi.block_max);
+    ensure_coarse(c, n, fi.block_max);
     size_t first[lz4b200_ctx::MAX_SLICES + 1];
     const int K = plan_slices(c, weight.data(), n, frame_bytes, true, first);
     if (int rc = ensure_events(c, K)) return rc;
