@@ -135,7 +135,7 @@ coarse_scan_kernel(const __grid_constant__ CoarseParams P)
     }
 }
 
-// all CTAs of the launch are resident (the grid is sized by occupancy): a counter that only grows is the barrier
+// all CTAs of the launch are resident (the grid is sized by occupancy and the launch is cooperative): a counter that only grows is the barrier
 __device__ __forceinline__ void coarse_grid_barrier(u32* counter, u32& round)
 {
     __syncthreads();
@@ -228,8 +228,11 @@ inline cudaError_t coarse_launch(const CoarseParams& P, int sm_count, cudaStream
     if (e != cudaSuccess) return e;
     if (per_sm < 1) per_sm = 1;
     if (per_sm > 2) per_sm = 2;                          // (the barrier needs every CTA resident: room is left for whatever else runs)
-    coarse_copy_kernel<<<(unsigned)(sm_count * per_sm), C_COPY_THREADS, 0, st>>>(P);
-    return cudaGetLastError();
+    // a cooperative launch: the runtime starts the kernel only when all its CTAs can be resident together (the barrier's premise)
+    CoarseParams Pc = P;
+    void* args[] = { (void*)&Pc };
+    e = cudaLaunchCooperativeKernel((const void*)coarse_copy_kernel, dim3((unsigned)(sm_count * per_sm)), dim3(C_COPY_THREADS), args, 0, st);
+    return e != cudaSuccess ? e : cudaGetLastError();
 }
 
 }  // namespace lz4b200
