@@ -31,7 +31,8 @@ struct CoarseParams {
     const u8* in; const u64* in_off; const u64* csz; const u64* out_off; const u64* usz; u8* out;
     u32* status; u32 n_chunks;
     u32 cap_all;                                   // see V5Params::cap_all (frames: the end-of-block rules are checked against the frame's block size)
-    uint4* desc;                                   // [n_chunks][C_MAXD]: x position in the chunk, y stream position (literals) / offset (match), z length, w bit 0: match, bits 8..: level
+    uint4* desc;                                   // [n_chunks][C_MAXD]: x position in the chunk, y stream position (literals) / position of the source period (match), z length, w bit 0: match, bits 8..: level
+    uint2* desc2;                                  // [n_chunks][C_MAXD], matches: x period d, y phase: out[x + i] = out[y_source + (phase + i) mod d]
     u32* ndesc;                                    // descriptors of the chunk (0: not taken)
     u32* list; u32* list_count;                    // chunks left to the team decoder
     u32* max_level;                                // highest level of the launch; behind it the grid barrier's counter
@@ -67,13 +68,15 @@ __device__ __forceinline__ bool coarse_read_length(const u8* src, u32 clen, u32&
 __global__ void __launch_bounds__(C_SCAN_WARPS * 32)
 coarse_scan_kernel(const __grid_constant__ CoarseParams P)
 {
-    __shared__ u32 s_pos[C_SCAN_WARPS][C_MAXD], s_len[C_SCAN_WARPS][C_MAXD], s_lvl[C_SCAN_WARPS][C_MAXD];   // matches of the chunk so far
+    __shared__ u32 s_pos[C_SCAN_WARPS][C_MAXD], s_len[C_SCAN_WARPS][C_MAXD], s_lvl[C_SCAN_WARPS][C_MAXD];   // matches of the chunk so far: output range, level,
+    __shared__ u32 s_src[C_SCAN_WARPS][C_MAXD], s_dph[C_SCAN_WARPS][C_MAXD];                               // ... source period (position; d | phase << 16)
     const u32 lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const u32 c = blockIdx.x * C_SCAN_WARPS + w;
     if (c >= P.n_chunks) return;
     const u8* src = P.in + P.in_off[c];
     const u64 clen64 = P.csz[c], n64 = P.usz[c];
     uint4* const d = P.desc + (size_t)c * C_MAXD;
+    uint2* const d2 = P.desc2 + (size_t)c * C_MAXD;
     u32 nd = 0, nm = 0, top = 0;
     bool take = false;
     if (clen64 == n64 && n64 != 0 && n64 < 0xFFFFFFFFull) {                 // raw chunk (_lzbench/lzbench.cpp:311-315): a plain copy
@@ -110,17 +113,32 @@ coarse_scan_kernel(const __grid_constant__ CoarseParams P)
             }
             m += MINMATCH;
             if (m > n || cpy + (u32)m + LASTLITERALS > capv || cpy + (u32)m > n || off == 0 || off > cpy) { take = false; break; }
-            // level: one above the highest earlier match whose output the source [cpy - off, cpy - off + min(off, m)) touches
+            // level: one above the highest earlier match whose output the source [cpy - off, cpy - off + min(off, m)) touches.
+            // FORWARDING: if the whole source lies inside the output of ONE earlier match k whose period divides this offset, the
+            // bytes are k's period again -- out[cpy + i] = out[src_k + (phase + i) mod d_k] -- so this match reads what k reads and
+            // runs in k's round (run-length data compressed in segments is a chain of such matches: one round instead of one each)
             const u32 s0 = cpy - off, s1 = s0 + (off < (u32)m ? off : (u32)m);
-            u32 lvl = 0;
-            for (u32 k = lane; k < nm; k += 32)
-                if (s_pos[w][k] < s1 && s_pos[w][k] + s_len[w][k] > s0 && s_lvl[w][k] > lvl) lvl = s_lvl[w][k];
+            u32 lvl = 0, fk = 0xFFFFFFFFu;
+            for (u32 k = lane; k < nm; k += 32) {
+                const u32 pk = s_pos[w][k], ek = pk + s_len[w][k];
+                if (pk < s1 && ek > s0 && s_lvl[w][k] > lvl) lvl = s_lvl[w][k];
+                if (pk <= s0 && s1 <= ek && off % (s_dph[w][k] & 0xFFFFu) == 0) fk = k;
+            }
             #pragma unroll
             for (u32 dd = 16; dd; dd >>= 1) { const u32 y = __shfl_xor_sync(FULL, lvl, dd); if (y > lvl) lvl = y; }
             lvl += 1;
+            const unsigned fm = __ballot_sync(FULL, fk != 0xFFFFFFFFu);
+            u32 srcp = s0, per = off, ph = 0;
+            if (fm) {
+                fk = __shfl_sync(FULL, fk, __ffs(fm) - 1);
+                per = s_dph[w][fk] & 0xFFFFu;
+                ph = ((s_dph[w][fk] >> 16) + (s0 - s_pos[w][fk])) % per;
+                srcp = s_src[w][fk]; lvl = s_lvl[w][fk];
+            }
             if (lane == 0) {
-                d[nd] = make_uint4(cpy, off, (u32)m, 1u | (lvl << 8));
-                s_pos[w][nm] = cpy; s_len[w][nm] = (u32)m; s_lvl[w][nm] = lvl;
+                d[nd] = make_uint4(cpy, srcp, (u32)m, 1u | (lvl << 8));
+                d2[nd] = make_uint2(per, ph);
+                s_pos[w][nm] = cpy; s_len[w][nm] = (u32)m; s_lvl[w][nm] = lvl; s_src[w][nm] = srcp; s_dph[w][nm] = per | (ph << 16);
             }
             __syncwarp();
             nd++; nm++;
@@ -186,15 +204,17 @@ coarse_copy_kernel(const __grid_constant__ CoarseParams P)
                         } else {
                             // out[p + i] = out[p - d + i mod d]: 16-byte stores once the target is aligned, sources byte by byte from
                             // the period in front of the match (L1 / L2 hits)
-                            const u32 dd = q.y;
-                            const u8* const per = dst - dd;
+                            const uint2 q2 = P.desc2[(size_t)c * C_MAXD + k];
+                            const u32 dd = q2.x;
+                            const u8* const per = P.out + P.out_off[c] + q.y;
+                            const u64 a0 = a + q2.y;                                 // phase of this piece's first byte
                             u8* const t = dst + a;
                             u32 head = (u32)((16 - (reinterpret_cast<uintptr_t>(t) & 15)) & 15);
                             if (head > len) head = len;
-                            if (tid < head) t[tid] = per[(a + tid) % dd];
+                            if (tid < head) t[tid] = per[(a0 + tid) % dd];
                             const u32 nvec = (len - head) >> 4;
                             for (u32 j = tid; j < nvec; j += C_COPY_THREADS) {
-                                u32 s = (u32)((a + head + (u64)j * 16) % dd);
+                                u32 s = (u32)((a0 + head + (u64)j * 16) % dd);
                                 u32 wv[4];
                                 #pragma unroll
                                 for (u32 kk = 0; kk < 4; kk++) {
@@ -206,7 +226,7 @@ coarse_copy_kernel(const __grid_constant__ CoarseParams P)
                                 *reinterpret_cast<uint4*>(t + head + (size_t)j * 16) = make_uint4(wv[0], wv[1], wv[2], wv[3]);
                             }
                             const u32 done = head + nvec * 16;
-                            if (tid < len - done) t[done + tid] = per[(a + done + tid) % dd];
+                            if (tid < len - done) t[done + tid] = per[(a0 + done + tid) % dd];
                         }
                     }
                 }

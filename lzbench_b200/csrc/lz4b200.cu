@@ -239,7 +239,7 @@ void ensure_coarse(lz4b200_ctx* c, size_t n, size_t max_chunk)
 {
     c->coarse_chunks = 0;
     if (!c->coarse_on || c->kernel_gen < 5 || max_chunk <= V7_MAX_CHUNK || n == 0) return;
-    if (c->coarse.ensure(1024 + n * (C_MAXD * sizeof(uint4) + 2 * sizeof(u32))) != cudaSuccess) { cudaGetLastError(); return; }
+    if (c->coarse.ensure(1024 + n * (C_MAXD * (sizeof(uint4) + sizeof(uint2)) + 2 * sizeof(u32))) != cudaSuccess) { cudaGetLastError(); return; }
     c->coarse_chunks = n;
 }
 
@@ -439,8 +439,9 @@ int decompress_slice(lz4b200_ctx* c, const u8* d_in, const u64* d_csz, const u64
         const size_t nt = c->coarse_chunks;
         CoarseParams P{ d_in, s.coff, d_csz, s.uoff, d_usz, d_out, s.status, (u32)n, cap_all,
                         (uint4*)(b + 1024) + s.first_chunk * C_MAXD,
-                        (u32*)(b + 1024 + nt * C_MAXD * sizeof(uint4)) + s.first_chunk,
-                        (u32*)(b + 1024 + nt * C_MAXD * sizeof(uint4)) + nt + s.first_chunk,
+                        (uint2*)(b + 1024 + nt * C_MAXD * sizeof(uint4)) + s.first_chunk * C_MAXD,
+                        (u32*)(b + 1024 + nt * C_MAXD * (sizeof(uint4) + sizeof(uint2))) + s.first_chunk,
+                        (u32*)(b + 1024 + nt * C_MAXD * (sizeof(uint4) + sizeof(uint2))) + nt + s.first_chunk,
                         (u32*)b + s.slice, (u32*)b + 64 + 2 * s.slice };
         // the copy kernel synchronises its CTAs through a counter, so all of them must be resident: two of them on two
         // streams (pipeline slices) could each hold the slots the other waits for -- one at a time per context

@@ -260,6 +260,56 @@ def test_coarse_chunks_decode_bit_exact(gpu_ctx, coarse):
         gpu_ctx.set_option("coarse", "1")
 
 
+def _build_block(seqs, last):
+    """An LZ4 block from (literals, offset, match length) triples and the last literals."""
+    def ext(v):
+        b = bytearray()
+        while v >= 255:
+            b.append(255); v -= 255
+        b.append(v)
+        return bytes(b)
+    out = bytearray()
+    for lit, off, ml in seqs:
+        out.append((min(len(lit), 15) << 4) | min(ml - 4, 15))
+        if len(lit) >= 15: out += ext(len(lit) - 15)
+        out += lit
+        out += bytes([off & 255, off >> 8])
+        if ml - 4 >= 15: out += ext(ml - 4 - 15)
+    out.append(min(len(last), 15) << 4)
+    if len(last) >= 15: out += ext(len(last) - 15)
+    out += last
+    return np.frombuffer(bytes(out), dtype=np.uint8).copy()
+
+
+def test_coarse_chunks_chained_matches(gpu_ctx):
+    """Hand-built blocks of long matches that read each other's output in every way the coarse path distinguishes: offsets that
+    the earlier match's period divides (forwarded: same round), offsets it does not divide (next round), sources that straddle
+    two matches, sources in literals, overlapping and non-overlapping matches; several chunks share the grid."""
+    rng = np.random.default_rng(41)
+    def lit(n): return bytes(rng.integers(0, 256, n, dtype=np.uint8))
+    blocks = [
+        [(lit(7), 7, 100000), (b"", 14, 80000), (b"", 10, 70000), (b"", 65000, 50000), (lit(3), 3, 90000), (b"", 60001, 66000)],
+        [(lit(1), 1, 300000), (b"", 255, 200000), (lit(300), 300, 65536), (b"", 600, 70000), (b"", 450, 80000)],
+        [(lit(70000), 65535, 65535), (b"", 65535, 131070), (lit(5), 5, 4), (b"", 9, 100000), (b"", 18, 100000), (b"", 27, 100000)],
+        [(lit(64), 64, 49088), (b"", 256, 49152), (b"", 192, 49152), (b"", 224, 49152), (b"", 160, 49152), (b"", 32, 49152)],
+    ]
+    packed, compr, cs, plain = [], [], [], []
+    for seqs in blocks:
+        blk = _build_block(seqs, lit(12))
+        n = sum(len(l) + m for l, _, m in seqs) + 12
+        r, out = O.oracle_decompress(blk, n)
+        assert r == n, (r, n)
+        if O.ref is not None:
+            r2, out2 = O.ref_decompress_safe(blk, n)
+            assert r2 == n and np.array_equal(out, out2)
+        packed.append(blk); compr.append(len(blk)); cs.append(n); plain.append(out)
+    for reps in (1, 3):                                  # few chunks (many CTAs per chunk) and some more
+        pk = np.concatenate(packed * reps)
+        out, r = gpu_ctx.decompress_batch(pk, np.asarray(compr * reps, dtype=np.uint64), np.asarray(cs * reps, dtype=np.uint64))
+        assert r == sum(cs) * reps
+        assert np.array_equal(out, np.concatenate(plain * reps))
+
+
 def test_coarse_chunks_corrupted_same_verdict_as_oracle(gpu_ctx):
     """Damaged blocks of the kind the coarse path takes: the same accept / reject decision as the oracle, and the oracle's
     bytes where it accepts (the coarse scan only ever accepts what passes every rule; the rest goes to the team decoder)."""
