@@ -44,14 +44,15 @@ constexpr u32 C3_NLONGQ = C3_TILE / C3_LONG_LIT + 2;
 constexpr u32 C3_NLONGM = 16;                    // long matches per half tile whose end is remembered
 constexpr u32 C3_NVR = 8;                        // warps of H and V
 constexpr u32 C3_NE = 4;                         // warps of E
-// Warp numbers.  The table warp and the parse warp are serial chains that everything else waits for, and a single warp running
-// through code nobody else runs lives on instruction fetch: they get scheduler 0 (warp number mod 4) to themselves, so that its
-// instruction cache holds their loops; warps 8 and 12 (the rest of that scheduler) exit at once.
+// Warp numbers.  The table warp and the two parse warps are serial chains that everything else waits for: they have scheduler 0
+// (warp number mod 4) to themselves -- tried against instruction fetch and issue competition, measured: no difference, their
+// instructions wait for each other, not for the scheduler.  Warp 12, the rest of that scheduler, has no stage: it helps with the
+// loading and clearing between chunks and takes part in the CTA barriers.
 constexpr u32 C3_WT = 0;
 constexpr u32 C3_WP = 4;
 constexpr u32 C3_WP2 = 8;                        // the second parse warp
 constexpr u32 C3_THREADS = 16 * 32;
-constexpr u32 C3_LIVE = (3 + C3_NVR + C3_NE) * 32;   // threads that take part in the CTA barrier
+constexpr u32 C3_LIVE = C3_THREADS;              // threads that share the work between chunks
 
 struct C3Smem {
     static constexpr u32 OFF_IN = 0;
@@ -150,10 +151,10 @@ compress_c3_kernel(const u8* __restrict__ in, const u64* __restrict__ in_off, co
     volatile u32* const s_misc = reinterpret_cast<volatile u32*>(smem + S::OFF_MISC + 16);   // [0] chunk [1] long-literal count [2] long-match count [3] chain state P has reached [5] final chain state [6] final output bytes
 
     const u32 tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    if (wid == 12) return;
+
     // H and V: 0 .. NVR-1, E: NVR .. NVR+NE-1 in the order of the warp numbers 1,2,3,5,6,7,9,10,11,13,14,15; the table and parse warps get large numbers
     const u32 warp = (wid & 3u) ? (wid >> 2) * 3 + (wid & 3u) - 1 : 0xFFFFu;
-    const u32 ltid = (wid & 3u) ? warp * 32 + lane : (C3_NVR + C3_NE + (wid >> 2)) * 32 + lane;   // dense thread number among the live ones
+    const u32 ltid = tid;                             // (warp 12 has no stage: it helps with the loading and clearing between chunks and takes part in the CTA barriers)
     u32 phase = 0;
     if (tid == 0) mbar_init(s_bar, 1);
     __syncthreads();
@@ -494,7 +495,7 @@ compress_c3_kernel(const u8* __restrict__ in, const u64* __restrict__ in_off, co
                         }
                         if (prof && lane == 0) atomicAdd((unsigned long long*)&prof[half ? 9 : 2], (unsigned long long)(clock64() - q0));
                     }
-                } else {
+                } else if (warp < C3_NVR + C3_NE) {
                     // ================= E of tile k - 4: one lane per sequence =================
                     const u32 t = k - 4, ew = warp - C3_NVR;
                     if (k >= 4 && t < n_tiles) {
