@@ -131,6 +131,7 @@ int lz4b200_debug_prof(lz4b200_ctx* ctx, uint64_t* out16);
  *   "split"    v7: percent of a large batch decoded by the team decoder on a second stream ("0" default; measured slower);
  *              "coarse" = "0"/"1" (default 1): chunks above 64 KiB that are a handful of long copies are decoded piecewise by the
  *              whole machine (kernels_coarse.cuh);
+ *              "v7big" = "0"/"1" (default 1): compressible chunks above 64 KiB (up to 16 MiB) through the sequence table too;
  *              "planes" = "8"/"16"/"32" chunks per warp in v7's table pass (default 32; measured: 16 the same, 8 slower)
  *   "timing" = "0"/"1" (see lz4b200_kernel_times_ms), "prof" = "0"/"1" (see lz4b200_debug_prof), "c1mode" (match-finder variant) */
 int lz4b200_set_option(lz4b200_ctx* ctx, const char* key, const char* value);

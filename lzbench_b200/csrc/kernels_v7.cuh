@@ -34,6 +34,10 @@ constexpr u32 V7_WIN = 4096;               // bytes of the per-warp output windo
 constexpr u32 V7_KEEP = 1008;              // history kept below a group when the window slides
 constexpr u32 V7_LPIECE = 8191;            // literal runs are cut into entries of at most this many bytes (13-bit field)
 constexpr u32 V7_MAX_CHUNK = 65536;
+constexpr u32 V7_BIG_MAX = 16u << 20;      // BIG variant (chunks above 64 KiB): the entries keep their 16-bit position fields, which then hold the low 16 bits --
+                                           // positions only grow along a chunk and by less than 65 536 per entry (matches are cut into pieces of V7_MPIECE),
+                                           // so pass 2 counts the wrap-arounds
+constexpr u32 V7_MPIECE = 32768;
 constexpr int V7_WARPS = 4;                // warps per CTA of the lane-per-sequence kernel
 constexpr u32 V7_STAGE = 512;              // stream bytes staged per group (one 16-byte block per lane; a group reads ~330)
 constexpr u32 V7_WARP_SMEM = 4096 + 32 + 2 * 512;    // V7_WIN + 32 + 2 * V7_STAGE
@@ -57,6 +61,7 @@ struct V7Params {
     u32* route;                            // V7_ROUTE_* per chunk
     u32* team_list; u32* team_count;       // chunks left to the team decoder
     u32* order; u32* bucket;               // pass 2 takes the chunks with the most sequences first: order[ticket], bucket counters u32[2][V7_BUCKETS]
+    const u32* skip;                       // optional: chunks with skip[c] != 0 are somebody else's (kernels_coarse.cuh has decoded them)
 };
 
 // entry, low word: bits 0-16 output position of the sequence, 17-29 literal count; high word: bits 0-15 stream position
@@ -106,7 +111,7 @@ __device__ __forceinline__ void v7_cp16(u8* smem_dst, const u8* gsrc)
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(d), "l"(gsrc) : "memory");
 }
 
-template <u32 LANES>                      // chunks per warp: 32 leaves one warp per scheduler on a 16 384-chunk batch; fewer lanes = more warps to interleave
+template <u32 LANES, bool BIG>            // LANES chunks per warp: 32 leaves one warp per scheduler on a 16 384-chunk batch; fewer lanes = more warps to interleave
 __global__ void __launch_bounds__(32)
 parse_v7_kernel(const __grid_constant__ V7Params P)
 {
@@ -122,9 +127,11 @@ parse_v7_kernel(const __grid_constant__ V7Params P)
         const u8* src = P.in + P.in_off[c];
         const u64 clen64 = P.csz[c], n64 = P.usz[c];
         const u64 base = v7_entries_for(P.out_off[c] - P.out_off[0], c);
-        if (clen64 == n64) {
+        if (BIG && P.skip && P.skip[c]) {
+            route = V7_ROUTE_NONE;                                        // decoded elsewhere; its status is set there
+        } else if (clen64 == n64) {
             route = n64 >= 4096 ? V7_ROUTE_TEAM : V7_ROUTE_SEQ;        // raw chunk (_lzbench/lzbench.cpp:311-315): a plain copy
-        } else if (n64 > V7_MAX_CHUNK || clen64 > 0xFFFFu || base + v7_entries_for(n64, 1) > P.table_cap ||
+        } else if (n64 > (BIG ? V7_BIG_MAX : V7_MAX_CHUNK) || clen64 > (BIG ? (u64)V7_BIG_MAX + (V7_BIG_MAX >> 7) : 0xFFFFull) || base + v7_entries_for(n64, 1) > P.table_cap ||
                    clen64 * 85 < n64 ||                                   // fewer than n / 256 sequences (>= 3 stream bytes each): the team decoder's case, no need to walk
                    clen64 + (n64 >> 5) >= n64) {                           // hardly compressed: long literal runs, the team decoder's case as well
             route = V7_ROUTE_TEAM;
@@ -197,7 +204,7 @@ parse_v7_kernel(const __grid_constant__ V7Params P)
             const u32 cpy_f = op + Lf, nop_f = cpy_f + ml_f;
             fast = tv && q <= qlim && cpy_f <= lim_cpy && nop_f <= lim_nop && !(lx && te1 == 255) && !(mx && m1 == 255);
             if (fast) {                                                   // (tv is only ever set in V7M_TOKEN)
-                tab[k++] = v7_pack(op, lsrc_f - mis, ml_f, Lf);
+                tab[k++] = BIG ? v7_pack(op & 0xFFFFu, (lsrc_f - mis) & 0xFFFFu, ml_f, Lf) : v7_pack(op, lsrc_f - mis, ml_f, Lf);
                 op = nop_f;
                 ip = ipn; tok = tokn; te1 = e1n; tv = ipn + 2 <= landed;
             }
@@ -240,11 +247,11 @@ parse_v7_kernel(const __grid_constant__ V7Params P)
             if (cpy > n) { err = ST_MATCH_END; break; }                  // (frame capacity > n) rejected below anyway; keeps the entry count bounded by n
             u32 ls = lsrc - mis, Lr = len, lop = op;
             while (Lr > V7_LPIECE) {                                     // literal-only pieces
-                tab[k++] = v7_pack(lop, ls, 0, V7_LPIECE);
+                tab[k++] = BIG ? v7_pack(lop & 0xFFFFu, ls & 0xFFFFu, 0, V7_LPIECE) : v7_pack(lop, ls, 0, V7_LPIECE);
                 lop += V7_LPIECE; ls += V7_LPIECE; Lr -= V7_LPIECE;
             }
             if (last) {
-                tab[k++] = v7_pack(lop, ls, 0, Lr);
+                tab[k++] = BIG ? v7_pack(lop & 0xFFFFu, ls & 0xFFFFu, 0, Lr) : v7_pack(lop, ls, 0, Lr);
                 op = cpy;
                 if (op != n) err = ST_SIZE;
                 break;
@@ -261,6 +268,14 @@ parse_v7_kernel(const __grid_constant__ V7Params P)
             }
             m += MINMATCH;
             if (op + m + LASTLITERALS > capv || op + m > n) { err = ST_MATCH_END; break; }
+            if (BIG) {                                                    // pieces of a long match: the same offset again (the two offset bytes follow the literals)
+                u32 mr = m;
+                while (mr > V7_MPIECE) {
+                    tab[k++] = v7_pack(lop & 0xFFFFu, ls & 0xFFFFu, V7_MPIECE, Lr);
+                    lop += Lr + V7_MPIECE; ls += Lr; Lr = 0; mr -= V7_MPIECE;
+                }
+                tab[k++] = v7_pack(lop & 0xFFFFu, ls & 0xFFFFu, mr, Lr);
+            } else
             tab[k++] = v7_pack(lop, ls, m, Lr);
             op += m;
             mode = V7M_TOKEN;
@@ -275,6 +290,7 @@ parse_v7_kernel(const __grid_constant__ V7Params P)
 #undef V7_RING_AT
 #undef V7_REQUEST
     if (!have) return;
+    if (BIG && P.skip && P.skip[c]) { P.nseq[c] = 0; P.route[c] = V7_ROUTE_NONE; atomicAdd(P.bucket, 1u); return; }
     if (!err && route == V7_ROUTE_SEQ && (u64)k * 256 < n) route = V7_ROUTE_TEAM;     // mostly long copies: the team decoder's case
     if (err) route = V7_ROUTE_NONE;
     P.status[c] = err;
@@ -320,6 +336,7 @@ __device__ __forceinline__ void v7_flush(u8* dstv, const u8* win, u32 win_base, 
     }
 }
 
+template <bool BIG>
 __global__ void __launch_bounds__(V7_WARPS * 32, 7)
 decompress_v7_kernel(const __grid_constant__ V7Params P)
 {
@@ -356,6 +373,7 @@ decompress_v7_kernel(const __grid_constant__ V7Params P)
         const u8* const srcA = src - mis;
         const u32 clenA = clen + mis;
         u32 sb = 0, sbuf = 0;              // the staged bytes are positions [sb, sb + V7_STAGE) in buffer sbuf
+        u32 obase = 0, lbase = 0, oprev = 0, lprev = 0;   // BIG: multiples of 65 536 the 16-bit fields have passed, and the fields of the last entry consumed
         {
             u8* st = stage0;
             if (lane * 16u < clenA) v7_cp16(st + lane * 16u, srcA + lane * 16u);
@@ -365,10 +383,22 @@ decompress_v7_kernel(const __grid_constant__ V7Params P)
         while (cur < ns) {
             const bool valid = cur + lane < ns;
             const u64 e = e_next;
-            const u32 op = ((u32)e & 0x1FFFFu) + A;
+            u32 op = ((u32)e & 0x1FFFFu) + A;
             const u32 L = (u32)e >> 17;
-            const u32 lsrc = (u32)(e >> 32) & 0xFFFFu;
+            u32 lsrc = (u32)(e >> 32) & 0xFFFFu;
             const u32 M = (u32)(e >> 48);
+            unsigned owrap = 0, lwrap = 0;
+            u32 o16 = 0, l16 = 0;
+            if (BIG) {                                                    // the fields hold the low 16 bits: count the wrap-arounds up to my entry
+                o16 = (u32)e & 0xFFFFu; l16 = lsrc;
+                u32 po = __shfl_up_sync(FULL, o16, 1), pl = __shfl_up_sync(FULL, l16, 1);
+                if (lane == 0) { po = oprev; pl = lprev; }
+                owrap = __ballot_sync(FULL, valid && o16 < po);
+                lwrap = __ballot_sync(FULL, valid && l16 < pl);
+                const unsigned upto = (2u << lane) - 1u;
+                op = obase + ((u32)__popc(owrap & upto) << 16) + o16 + A;
+                lsrc = lbase + ((u32)__popc(lwrap & upto) << 16) + l16;
+            }
             const u32 opn = op + L + M;
             // the literals and the offset of this lane: from the staged bytes if they are all there, else from global memory
             asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -384,6 +414,12 @@ decompress_v7_kernel(const __grid_constant__ V7Params P)
             const unsigned stop = __ballot_sync(FULL, !valid || lng || opn - op0 > V7_SPAN);
             const u32 k = stop ? (u32)__ffs(stop) - 1u : 32u;          // lanes [0, k) form the group
             const bool lng_k = k < 32 && __shfl_sync(FULL, (u32)lng, k & 31);       // ... and a long sequence follows it
+            if (BIG) {                                                    // the entries this iteration consumes move the bases on
+                const u32 used = k + (lng_k ? 1u : 0u);                  // (at least 1)
+                const unsigned um = used >= 32 ? FULL : ((1u << used) - 1u);
+                obase += (u32)__popc(owrap & um) << 16; lbase += (u32)__popc(lwrap & um) << 16;
+                oprev = __shfl_sync(FULL, o16, used - 1); lprev = __shfl_sync(FULL, l16, used - 1);
+            }
             {   // the next group's entries and stream bytes: on their way while this one is executed
                 const u32 nx = cur + k + (lng_k ? 1u : 0u) + lane;
                 e_next = nx < ns ? tab[nx] : 0ull;
@@ -555,32 +591,39 @@ decompress_v7_kernel(const __grid_constant__ V7Params P)
     }
 }
 
-inline cudaError_t v7_launch_parse(const V7Params& P, cudaStream_t st, int lanes = 32)
+inline cudaError_t v7_launch_parse(const V7Params& P, cudaStream_t st, int lanes = 32, bool big = false)
 {
     // P.bucket points at the slice's zero block: [0, 2 V7_BUCKETS) counters, then team_count, ticket of pass 2, ticket of the team decoder
     cudaError_t e = cudaMemsetAsync(P.bucket, 0, V7_ZERO_WORDS * sizeof(u32), st);
     if (e != cudaSuccess) return e;
-    if (lanes == 8) parse_v7_kernel<8><<<(P.n_chunks + 7) / 8, 32, 0, st>>>(P);
-    else if (lanes == 16) parse_v7_kernel<16><<<(P.n_chunks + 15) / 16, 32, 0, st>>>(P);
-    else parse_v7_kernel<32><<<(P.n_chunks + 31) / 32, 32, 0, st>>>(P);
+    if (big) parse_v7_kernel<32, true><<<(P.n_chunks + 31) / 32, 32, 0, st>>>(P);
+    else if (lanes == 8) parse_v7_kernel<8, false><<<(P.n_chunks + 7) / 8, 32, 0, st>>>(P);
+    else if (lanes == 16) parse_v7_kernel<16, false><<<(P.n_chunks + 15) / 16, 32, 0, st>>>(P);
+    else parse_v7_kernel<32, false><<<(P.n_chunks + 31) / 32, 32, 0, st>>>(P);
     order_v7_kernel<<<(P.n_chunks + 255) / 256, 256, 0, st>>>(P);
     return cudaGetLastError();
 }
 
-inline cudaError_t v7_launch_decompress(const V7Params& P, int sm_count, cudaStream_t st)
+template <bool BIG>
+inline cudaError_t v7_launch_decompress_t(const V7Params& P, int sm_count, cudaStream_t st)
 {
     int per_sm = 0;
     const size_t smem = (size_t)V7_WARPS * V7_WARP_SMEM;
-    cudaError_t e = cudaFuncSetAttribute(decompress_v7_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   // per device: every launch
+    cudaError_t e = cudaFuncSetAttribute(decompress_v7_kernel<BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   // per device: every launch
     if (e != cudaSuccess) return e;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, decompress_v7_kernel, V7_WARPS * 32, smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, decompress_v7_kernel<BIG>, V7_WARPS * 32, smem);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) per_sm = 1;
     unsigned grid = (unsigned)(sm_count * per_sm);
     const unsigned need = (P.n_chunks + V7_WARPS - 1) / V7_WARPS;
     if (grid > need) grid = need;
-    decompress_v7_kernel<<<grid, V7_WARPS * 32, smem, st>>>(P);               // (P.ticket was cleared with the zero block)
+    decompress_v7_kernel<BIG><<<grid, V7_WARPS * 32, smem, st>>>(P);               // (P.ticket was cleared with the zero block)
     return cudaGetLastError();
+}
+
+inline cudaError_t v7_launch_decompress(const V7Params& P, int sm_count, cudaStream_t st, bool big = false)
+{
+    return big ? v7_launch_decompress_t<true>(P, sm_count, st) : v7_launch_decompress_t<false>(P, sm_count, st);
 }
 
 }  // namespace lz4b200

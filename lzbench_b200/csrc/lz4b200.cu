@@ -136,6 +136,7 @@ struct lz4b200_ctx {
     DevBuf coarse;                      // coarse decode (kernels_coarse.cuh): list counters per slice, descriptors, descriptor counts, work list
     size_t coarse_chunks = 0;           // chunk count its arrays are laid out for (current call; 0: not available)
     bool coarse_on = true;              // option "coarse"
+    bool v7_big = true;                 // option "v7big": chunks above 64 KiB (up to 16 MiB) through the sequence table as well
     cudaEvent_t ev_coarse = nullptr;    // the last coarse copy kernel of this context (they run one at a time)
     DevBuf v7_table, v7_u32;            // v7 decode: sequence table (u64 entries) and nseq / route / team list (u32[3][n_chunks])
     size_t v7_chunks = 0;               // chunk count the u32 arrays are laid out for (current call)
@@ -227,7 +228,7 @@ constexpr size_t V7_SUB = 65536;            // chunks per sub-batch of a device-
 void ensure_v7(lz4b200_ctx* c, size_t n, size_t table_chunks, size_t max_chunk)
 {
     c->v7_chunks = c->v7_table_chunks = 0;
-    if (c->kernel_gen != 7 || max_chunk > V7_MAX_CHUNK || max_chunk < c->v7_min_chunk || n == 0) return;
+    if (c->kernel_gen != 7 || max_chunk > V7_BIG_MAX || (max_chunk > V7_MAX_CHUNK && !c->v7_big) || max_chunk < c->v7_min_chunk || n == 0) return;
     c->v7_per_chunk = (size_t)v7_entries_for(max_chunk, 1) + 2;      // + 2: the floors of a ragged prefix sum
     if (c->v7_u32.ensure((4 * n + V7_ZERO_WORDS * lz4b200_ctx::MAX_SLICES) * sizeof(u32)) != cudaSuccess ||
         c->v7_table.ensure(table_chunks * c->v7_per_chunk * sizeof(u64)) != cudaSuccess) { cudaGetLastError(); return; }
@@ -417,7 +418,7 @@ int decompress_slice(lz4b200_ctx* c, const u8* d_in, const u64* d_csz, const u64
             const size_t b2 = b + mA, m2 = m - mA;
             if (m2) {
                 V7Params P{ d_in, s.coff + b2, d_csz + b2, s.uoff + b2, d_usz + b2, d_out, s.status + b2, d_bad, s.v7_count + 1, (u32)m2, cap_all,
-                            s.v7_table, s.v7_cap, s.v7_nseq + b2, s.v7_route + b2, s.v7_list + b2, s.v7_count, s.v7_order + b2, s.v7_bucket };
+                            s.v7_table, s.v7_cap, s.v7_nseq + b2, s.v7_route + b2, s.v7_list + b2, s.v7_count, s.v7_order + b2, s.v7_bucket, nullptr };
                 CU(v7_launch_parse(P, st, c->v7_lanes));
                 if (mA) {
                     CU(v5_launch_decompress(16, d_in, s.coff + b, d_csz + b, s.uoff + b, d_usz + b, d_out, s.status + b, d_bad, (u32)mA,
@@ -449,9 +450,22 @@ int decompress_slice(lz4b200_ctx* c, const u8* d_in, const u64* d_csz, const u64
         else CU(cudaStreamWaitEvent(st, c->ev_coarse, 0));
         CU(coarse_launch(P, c->sm_count, st));
         CU(cudaEventRecord(c->ev_coarse, st));
-        CU(v5_launch_decompress(team == 32 ? 16 : team, d_in, s.coff, d_csz, s.uoff, d_usz, d_out, s.status, d_bad, (u32)n,
-                                s.ticket, c->sm_count, st, cap_all, P.list, P.list_count));
-        c->launches += 3;
+        if (s.v7_table && n <= V7_SUB && max_chunk <= V7_BIG_MAX) {
+            // ... and the rest (compressible data) goes through the sequence table as 64 KiB chunks do: one lane per chunk
+            // walks the chain (the entries keep their 16-bit fields, pass 2 counts the wrap-arounds), one lane per sequence
+            // copies; what the table cannot hold is left to the team decoder
+            V7Params Q{ d_in, s.coff, d_csz, s.uoff, d_usz, d_out, s.status, d_bad, s.v7_count + 1, (u32)n, cap_all,
+                        s.v7_table, s.v7_cap, s.v7_nseq, s.v7_route, s.v7_list, s.v7_count, s.v7_order, s.v7_bucket, P.ndesc };
+            CU(v7_launch_parse(Q, st, 32, true));
+            CU(v7_launch_decompress(Q, c->sm_count, st, true));
+            CU(v5_launch_decompress(team == 32 ? 16 : team, d_in, s.coff, d_csz, s.uoff, d_usz, d_out, s.status, d_bad, (u32)n,
+                                    s.v7_count + 2, c->sm_count, st, cap_all, s.v7_list, s.v7_count, true));
+            c->launches += 7;
+        } else {
+            CU(v5_launch_decompress(team == 32 ? 16 : team, d_in, s.coff, d_csz, s.uoff, d_usz, d_out, s.status, d_bad, (u32)n,
+                                    s.ticket, c->sm_count, st, cap_all, P.list, P.list_count));
+            c->launches += 3;
+        }
     } else if (c->kernel_gen >= 7) {
         CU(v5_launch_decompress(team == 32 ? 16 : team, d_in, s.coff, d_csz, s.uoff, d_usz, d_out, s.status, d_bad, (u32)n,
                                 s.ticket, c->sm_count, st, cap_all));
@@ -736,6 +750,7 @@ int lz4b200_set_option(lz4b200_ctx* c, const char* key, const char* value)
         if (p >= -1 && p <= 90) { c->split = p; return 0; }
     }
     if (!strcmp(key, "coarse")) { c->coarse_on = value[0] == '1'; return 0; }
+    if (!strcmp(key, "v7big")) { c->v7_big = value[0] == '1'; return 0; }
     if (!strcmp(key, "planes")) { const int v = atoi(value); if (v == 8 || v == 16 || v == 32) { c->v7_lanes = v; return 0; } return -1; }
     if (!strcmp(key, "ramp")) { c->ramp = value[0] == '1'; return 0; }
     if (!strcmp(key, "h2d")) { c->own_h2d = strcmp(value, "shared") != 0; return 0; }

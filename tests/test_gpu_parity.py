@@ -341,6 +341,47 @@ def test_coarse_chunks_corrupted_same_verdict_as_oracle(gpu_ctx):
                 assert np.array_equal(out[i], ref_out), i
 
 
+@pytest.mark.parametrize("v7big", ["1", "0"])
+def test_large_compressible_chunks_and_their_corruptions(gpu_ctx, v7big):
+    """Chunks above 64 KiB of compressible data go through the sequence table too (kernels_v7.cuh, BIG: 16-bit position fields
+    whose wrap-arounds pass 2 counts, long matches in pieces): bit-exact on reference blocks of several sizes, and the oracle's
+    verdict (and bytes) on damaged ones."""
+    gpu_ctx.set_option("v7big", v7big)
+    try:
+        rng = np.random.default_rng(43)
+        sizes = np.asarray([65537, 70000, 131072, 200001, 1 << 20, 3 << 20], dtype=np.uint64)
+        data = L.corpus("mixed", int(sizes.sum()), seed=9)
+        long_run = np.zeros(400000, dtype=np.uint8); long_run[::1000] = 7         # matches far above 32 768 bytes between text
+        data[300000:700000] = long_run
+        packed, compr = O.oracle_chunked_compress(data, sizes)
+        out, r = gpu_ctx.decompress_batch(packed, compr, sizes)
+        assert r == len(data) and np.array_equal(out, data)
+        p2, c2, t2 = gpu_ctx.compress_batch(data, sizes)
+        out, r = gpu_ctx.decompress_batch(p2[:t2], c2, sizes)
+        assert r == len(data) and np.array_equal(out, data)
+        n = 150000
+        plain = data[:n]
+        good = O.oracle_compress(plain)
+        blocks, expect = [], []
+        for _ in range(64):
+            bad = good.copy()
+            for _ in range(int(rng.integers(1, 4))):
+                bad[int(rng.integers(0, len(bad)))] = int(rng.integers(0, 256))
+            blocks.append(bad)
+            rr, oo = O.oracle_decompress(bad, n)
+            expect.append((rr == n, oo))
+        pk = np.concatenate(blocks)
+        out, r = gpu_ctx.decompress_batch(pk, np.full(len(blocks), len(good), dtype=np.uint64), np.full(len(blocks), n, dtype=np.uint64))
+        n_bad = sum(1 for ok, _ in expect if not ok)
+        assert (r == -n_bad) if n_bad else (r == n * len(blocks))
+        out = out.reshape(len(blocks), n)
+        for i, (ok, oo) in enumerate(expect):
+            if ok:
+                assert np.array_equal(out[i], oo), i
+    finally:
+        gpu_ctx.set_option("v7big", "1")
+
+
 @pytest.mark.parametrize("kernels", ["v0", "v1", "v2", "v3", "v4", "v5", "v6", "v7"])
 def test_plugin_signature_wrappers(gpu_ctx, kernels):
     """lzbench_lz4_b200_{init,compress,decompress,deinit}: the unpatched-harness path, one chunk per call."""
