@@ -10,14 +10,14 @@ ncu -i $O/prof_${R}_final_parse_v7.ncu-rep --page raw --csv > /tmp/r1.csv 2>/dev
 cat /tmp/r1.csv /tmp/r2.csv > $P/${R}_decompress_v7_ncu_raw.csv
 ncu -i $O/prof_${R}_final_compress_c3.ncu-rep --page details > $P/${R}_compress_c3_ncu_details.txt 2>/dev/null
 ncu -i $O/prof_${R}_final_compress_c3.ncu-rep --page raw --csv > $P/${R}_compress_c3_ncu_raw.csv 2>/dev/null
-python scripts/ncu_by_line.py $O/prof_${R}_final_parse_v7.ncu-rep parse_v7_kernel 45 > $P/${R}_parse_v7_by_source_line.txt
-python scripts/ncu_by_line.py $O/prof_${R}_final_decompress_v7.ncu-rep decompress_v7 60 > $P/${R}_decompress_v7_by_source_line.txt
+python scripts/ncu_by_line.py $O/prof_${R}_final_parse_v7.ncu-rep parse_v7_kernel:parse_v7_kernelILj32ELb0 45 > $P/${R}_parse_v7_by_source_line.txt
+python scripts/ncu_by_line.py $O/prof_${R}_final_decompress_v7.ncu-rep decompress_v7:decompress_v7_kernelILb0 60 > $P/${R}_decompress_v7_by_source_line.txt
 python scripts/ncu_by_line.py $O/prof_${R}_final_compress_c3.ncu-rep compress_c3:compress_c3_kernelILb0 70 > $P/${R}_compress_c3_by_source_line.txt
 cuobjdump -sass lzbench_b200/_lib/liblz4b200.so > /tmp/all.sass
 python - <<'EOF'
 import re
 txt = open('/tmp/all.sass').read()
-want = {'compress_c3_kernelILb0': 'compress_c3.sass', 'parse_v7_kernelILj32': 'parse_v7.sass', '20decompress_v7_kernel': 'decompress_v7.sass',
+want = {'compress_c3_kernelILb0': 'compress_c3.sass', 'parse_v7_kernelILj32ELb0': 'parse_v7.sass', 'decompress_v7_kernelILb0': 'decompress_v7.sass',
         'order_v7_kernel': 'order_v7.sass', 'coarse_scan_kernel': 'coarse_scan.sass', 'coarse_copy_kernel': 'coarse_copy.sass'}
 for p in re.split(r'(?=\n\s*Function : )', txt):
     m = re.search(r'Function : (\S+)', p)
