@@ -368,7 +368,7 @@ def run_b200(args):
     # (profiles/README.md), valid for the default workload only (1 GiB mixed, 64 KiB chunks, default kernels)
     default_cfg = args.size_mib == 1024 and chunk == 65536 and args.corpus == "mixed" and not args.kernels
     traffic = {"decompress": 3.5969e9 if default_cfg else None,          # profiles/r02_decompress_v7_ncu_raw.csv: table pass 0.415 + 0.483, lane-per-sequence pass 1.662 + 1.037 GB
-               "compress": 1.6975e9 if default_cfg else None}            # profiles/r02_compress_c3_ncu_raw.csv: 1.076 + 0.621 GB
+               "compress": 1.6950e9 if default_cfg else None}            # profiles/r02_compress_c3_ncu_raw.csv: 1.076 + 0.619 GB
 
     def roof(kt, which):
         if not kt:
