@@ -448,7 +448,16 @@ int decompress_slice(lz4b200_ctx* c, const u8* d_in, const u64* d_csz, const u64
         // streams (pipeline slices) could each hold the slots the other waits for -- one at a time per context
         if (!c->ev_coarse) CU(cudaEventCreateWithFlags(&c->ev_coarse, cudaEventDisableTiming));
         else CU(cudaStreamWaitEvent(st, c->ev_coarse, 0));
-        CU(coarse_launch(P, c->sm_count, st));
+        const cudaError_t ce = coarse_launch(P, c->sm_count, st);
+        if (ce != cudaSuccess) {
+            // (a cooperative launch the device cannot hold: the descriptors are dropped, the team decoder takes every chunk,
+            // and this context stops trying)
+            cudaGetLastError();
+            c->coarse_on = false;
+            CU(v5_launch_decompress(team == 32 ? 16 : team, d_in, s.coff, d_csz, s.uoff, d_usz, d_out, s.status, d_bad, (u32)n,
+                                    s.ticket, c->sm_count, st, cap_all));
+            c->launches += 3;
+        } else {
         CU(cudaEventRecord(c->ev_coarse, st));
         if (s.v7_table && n <= V7_SUB && max_chunk <= V7_BIG_MAX) {
             // ... and the rest (compressible data) goes through the sequence table as 64 KiB chunks do: one lane per chunk
@@ -465,6 +474,7 @@ int decompress_slice(lz4b200_ctx* c, const u8* d_in, const u64* d_csz, const u64
             CU(v5_launch_decompress(team == 32 ? 16 : team, d_in, s.coff, d_csz, s.uoff, d_usz, d_out, s.status, d_bad, (u32)n,
                                     s.ticket, c->sm_count, st, cap_all, P.list, P.list_count));
             c->launches += 3;
+        }
         }
     } else if (c->kernel_gen >= 7) {
         CU(v5_launch_decompress(team == 32 ? 16 : team, d_in, s.coff, d_csz, s.uoff, d_usz, d_out, s.status, d_bad, (u32)n,
